@@ -1,0 +1,258 @@
+# -*- coding: utf-8 -*-
+"""
+ctypes binding of ``include/tricolour_b200.h`` (libtricolour_b200.so).
+
+The library is the hand-written sm_100a CUDA implementation; there is no other
+implementation behind this module.  If the shared object has not been built
+(``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C tricolour_b200/csrc``) or no GPU is visible, calls raise
+``RuntimeError`` -- nothing falls back to the CPU.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtricolour_b200.so")
+
+TC_OK, TC_ERR_VALUE, TC_ERR_CUDA, TC_ERR_NOGPU = 0, 1, 2, 3
+HOST, DEVICE = 0, 1
+VIS_COMPLEX64, VIS_FLOAT32 = 0, 1
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+
+
+class StParams(ctypes.Structure):
+    """mirror of ``tc_st_params``"""
+    _fields_ = [
+        ("outlier_nsigma", _dbl),
+        ("nwin_time", _i32),
+        ("nwin_freq", _i32),
+        ("windows_time", _vp),
+        ("tf_time", _vp),
+        ("scale_time", _vp),
+        ("windows_freq", _vp),
+        ("tf_freq", _vp),
+        ("scale_freq", _vp),
+        ("background_reject", _dbl),
+        ("background_iterations", _i32),
+        ("nchunk_ends", _i32),
+        ("radii_spec", _vp),
+        ("radii_2d", _vp),
+        ("freq_chunk_ends", _vp),
+        ("time_extend", _i64),
+        ("freq_extend", _i64),
+        ("average_freq", _i64),
+        ("flag_all_time_frac", _dbl),
+        ("flag_all_freq_frac", _dbl),
+        ("num_major_iterations", _i32),
+        ("reserved", _i32),
+    ]
+
+
+_SIGNATURES = {
+    "tc_last_error": (ctypes.c_char_p, []),
+    "tc_device_count": (_int, []),
+    "tc_context_create": (_int, [_int, _vp, ctypes.POINTER(_vp)]),
+    "tc_context_destroy": (None, [_vp]),
+    "tc_synchronize": (_int, [_vp]),
+    "tc_launch_count": (ctypes.c_ulonglong, [_vp]),
+    "tc_workspace_peak": (ctypes.c_size_t, [_vp]),
+    "tc_alloc_pinned": (_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "tc_free_pinned": (_int, [_vp]),
+    "tc_is_emulated": (_int, []),
+    "tc_flag_nans_zeros": (_int, [_vp, _vp, _vp, _vp, _i64, _int]),
+    "tc_flag_autos": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _int]),
+    "tc_apply_channel_mask": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _vp, _int]),
+    "tc_sum_threshold": (_int, [_vp, ctypes.POINTER(StParams), _vp, _int, _vp, _i64, _i64, _i64, _vp, _int]),
+    "tc_uvcontsub": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _int, _dbl, _vp, _int]),
+    "tc_polarised_intensity": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp, _int]),
+    "tc_unpolarised_intensity": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _int, _vp, _int]),
+    "tc_pack": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _int]),
+    "tc_unpack": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int]),
+    "tc_unpack_flags_any_corr": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int]),
+    "tc_window_counts": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int]),
+    "tc_flags_or": (_int, [_vp, _vp, _vp, _vp, _i64, _int]),
+    "tc_stage_average_freq": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int]),
+    "tc_stage_time_median": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _int]),
+    "tc_stage_chunk_median_abs": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _int]),
+    "tc_stage_masked_filter": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _int]),
+    "tc_stage_interp_nans": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
+    "tc_stage_background2d": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _dbl, _vp, _int, _vp, _int]),
+    "tc_stage_sum_threshold": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _int, _dbl, _vp,
+                                      _int, _vp, _int]),
+    "tc_stage_combine_unaverage": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _dbl,
+                                          _dbl, _vp, _int]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def _bind(lib):
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load(path=None):
+    """Load (once) and return the CUDA library.  Fails loudly when missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise RuntimeError(
+                "tricolour_b200: CUDA library %s not found. Build it with "
+                "`make -C tricolour_b200/csrc` (nvcc, sm_100a). There is no CPU "
+                "fallback." % p)
+        lib = _bind(ctypes.CDLL(p))
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _set_library_for_testing(lib):
+    """tests/ only: route the host logic through another build of the same
+    C ABI (the CPU-emulated kernels).  Never used by the package itself."""
+    global _lib
+    _lib = lib
+    _tls.__dict__.clear()
+
+
+def check(rc):
+    if rc == TC_OK:
+        return
+    msg = load().tc_last_error()
+    msg = msg.decode("utf-8", "replace") if msg else "unknown error"
+    if rc == TC_ERR_VALUE:
+        raise ValueError(msg)
+    raise RuntimeError("tricolour_b200: " + msg)
+
+
+class Context(object):
+    """Owns a ``tc_context`` (stream + workspace).  One per thread."""
+
+    def __init__(self, device=None, stream=None):
+        lib = load()
+        if device is None:
+            device = default_device()
+        h = _vp()
+        check(lib.tc_context_create(int(device), _vp(stream) if stream else None,
+                                    ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.stream = stream
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(load().tc_synchronize(self._h))
+
+    def launch_count(self):
+        return int(load().tc_launch_count(self._h))
+
+    def workspace_peak(self):
+        return int(load().tc_workspace_peak(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().tc_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_device():
+    for key in ("TRICOLOUR_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v is not None and v != "":
+            return int(v)
+    return 0
+
+
+_tls = threading.local()
+
+
+def get_context(device=None, stream=None):
+    """Thread-local context for (device, stream); the reference is called from a
+    dask ThreadPool, so every worker thread gets its own stream and arena."""
+    if device is None:
+        device = default_device()
+    key = (int(device), int(stream) if stream else 0)
+    cache = _tls.__dict__.setdefault("ctx", {})
+    ctx = cache.get(key)
+    if ctx is None:
+        ctx = Context(device, stream)
+        cache[key] = ctx
+    return ctx
+
+
+# ---------------------------------------------------------------------------
+# array plumbing: numpy arrays (host) or torch CUDA tensors (device)
+# ---------------------------------------------------------------------------
+def is_device_array(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if is_device_array(a):
+        return _vp(a.data_ptr())
+    return _vp(a.ctypes.data)
+
+
+def context_for(*arrays):
+    """Host arrays -> thread default context; device tensors -> a context bound
+    to torch's current stream on the tensors' device."""
+    for a in arrays:
+        if is_device_array(a):
+            import torch
+            dev = a.device.index if a.device.index is not None else torch.cuda.current_device()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            return get_context(dev, stream), DEVICE
+    return get_context(), HOST
+
+
+_pinned = {}
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (fast H2D/D2H staging).
+    The block lives until ``free_pinned(arr)`` or process exit."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    n = count * dtype.itemsize
+    p = _vp()
+    check(lib.tc_alloc_pinned(n, ctypes.byref(p)))
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    _pinned[p.value] = buf
+    return arr
+
+
+def free_pinned(arr):
+    addr = arr.ctypes.data
+    if _pinned.pop(addr, None) is not None:
+        check(load().tc_free_pinned(_vp(addr)))

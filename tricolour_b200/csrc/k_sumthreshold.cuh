@@ -1,0 +1,304 @@
+// k_sumthreshold.cuh -- the remaining stages of _get_baseline_flags
+// (flagging.py:921-976): amplitude/averaging prep, NaN interpolation, the 1-D
+// SumThreshold scans and the flag combination / dilation / fraction rules.
+#pragma once
+#include "tc_common.cuh"
+
+// ----------------------------------------------------------------------------
+// S1 _average_freq (flagging.py:819-875)
+// |complex64| is numba's hypotf: (float) sqrt((double)re*re + (double)im*im)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float tc_abs_c64(float re, float im)
+{
+    if (isinf(re) || isinf(im)) return INFINITY;
+    double dr = (double)re, di = (double)im;
+    // both products are exact in float64, so one rounding happens in the add
+    return (float)__dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(di, di)));
+}
+
+// one thread per averaged sample (cp, t, fa); output in (cp, T, Fa) layout
+__global__ void __launch_bounds__(256)
+k_prep(const void *__restrict__ vis, int vis_kind, const u8 *__restrict__ flags,
+       int64_t total_out, int F, int Fa, int factor, float *__restrict__ out_data,
+       u8 *__restrict__ out_flags)
+{
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total_out) return;
+    int64_t row = o / Fa;
+    int fa = (int)(o - row * Fa);
+    int f0 = fa * factor;
+    int f1 = f0 + factor < F ? f0 + factor : F;
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int f = f0; f < f1; f++) {
+        int64_t i = row * F + f;
+        float a;
+        if (vis_kind == TC_VIS_COMPLEX64) {
+            float2 v = ((const float2 *)vis)[i];
+            a = tc_abs_c64(v.x, v.y);
+        } else {
+            a = fabsf(((const float *)vis)[i]);
+        }
+        if (!flags[i] && !(a != a)) { sum = __fadd_rn(sum, a); cnt++; }
+    }
+    if (cnt == 0) { out_data[o] = 0.0f; out_flags[o] = 1; }
+    else { out_data[o] = __fdiv_rn(sum, (float)cnt); out_flags[o] = 0; }
+}
+
+// flags[(cp,t,f)] |= spec[(cp,f)]   (flagging.py:954)
+__global__ void __launch_bounds__(256)
+k_or_spec(u8 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total, int T, int Fa)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t row = i / Fa;
+    int f = (int)(i - row * Fa);
+    int64_t cp = row / T;
+    if (spec[cp * Fa + f]) flags[i] = 1;
+}
+
+// out = a - b elementwise
+__global__ void __launch_bounds__(256)
+k_sub(const float *a, const float *b, float *out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = a[i] - b[i];
+}
+
+// out = a | b for byte flags
+__global__ void __launch_bounds__(256)
+k_or_bytes(const u8 *__restrict__ a, const u8 *__restrict__ b, u8 *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (u8)((a[i] | b[i]) ? 1 : 0);
+}
+
+// ----------------------------------------------------------------------------
+// S5 _linearly_interpolate_nans (flagging.py:307-359): one thread per line,
+// line element i at base + i*stride (lines are the frequency axis).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_interp_nans(float *__restrict__ d, int64_t nlines, int64_t ninner, int64_t outer_stride,
+              int64_t inner_stride, int n, int64_t stride)
+{
+    int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nlines) return;
+    int64_t outer = line / ninner, inner = line - outer * ninner;
+    float *x = d + outer * outer_stride + inner * inner_stride;
+#define X(i) x[(int64_t)(i) * stride]
+    int p = 0;
+    while (p < n && X(p) != X(p)) p++;
+    if (p == n) {
+        for (int i = 0; i < n; i++) X(i) = 0.0f;
+        return;
+    }
+    float first = X(p);
+    for (int i = 0; i < p; i++) X(i) = first;  // extrapolate backwards
+    p += 1;
+    while (p < n) {
+        float cur = X(p);
+        if (cur != cur) {
+            int q = p + 1;
+            while (q < n && X(q) != X(q)) q++;
+            float start = X(p - 1);
+            if (q == n) {
+                for (int i = p; i < n; i++) X(i) = start;  // extrapolate forwards
+            } else {
+                // float32 difference, true division by an int64 -> float64
+                double grad = __ddiv_rn((double)(X(q) - start), (double)(q - (p - 1)));
+                for (int i = p; i < q; i++)
+                    X(i) = (float)__dadd_rn((double)start, __dmul_rn((double)(i - (p - 1)), grad));
+            }
+            p = q;
+        } else {
+            p += 1;
+        }
+    }
+#undef X
+}
+
+// ----------------------------------------------------------------------------
+// S9 _sum_threshold1d (flagging.py:610-681) with _convolve_flags (582-607).
+// One thread scans one (line, chunk): for every window, a sequential float64
+// prefix sum of the clamped samples over the padded chunk, window sums as
+// prefix differences, and smearing of every flagged window over its samples.
+// Samples of a line: data[base + i*estride]; neighbouring threads own
+// neighbouring lines (stride 1), so every access is coalesced.
+// Scratch per thread: a float64 prefix ring and one byte of pos/neg state per
+// padded sample, both laid out [chunk][sample][line] like the data.
+// ----------------------------------------------------------------------------
+#define TC_MAX_WINDOWS 16
+struct StScanArgs {
+    const float *data;
+    const float *thr;         // [line*nchunks + chunk] float32 thresholds (inf = none)
+    u8 *out;                  // same layout as data
+    int64_t nlines;           // total lines (all planes)
+    int64_t ninner;           // lines per plane (contiguous)
+    int64_t outer_stride;     // plane stride in samples
+    int64_t estride;          // distance between consecutive samples of a line (= ninner)
+    int n;                    // line length
+    int nchunks;
+    const int64_t *chunk_ends;  // device [nchunks+1]
+    int nwin;
+    int maxw;
+    int64_t windows[TC_MAX_WINDOWS];
+    double tf[TC_MAX_WINDOWS];
+    float scale[TC_MAX_WINDOWS];
+    int mpad;                 // max padded chunk length
+    double *cum;              // [nplanes][nchunks][mpad+1][ninner]
+    u8 *pn;                   // [nplanes][nchunks][mpad][ninner]
+};
+
+__global__ void __launch_bounds__(128)
+k_st_scan(StScanArgs a)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nlines * a.nchunks) return;
+    // thread order: (plane, chunk, inner) so that a warp shares plane and chunk
+    int64_t per_plane = (int64_t)a.nchunks * a.ninner;
+    int64_t plane = g / per_plane;
+    int64_t rem = g - plane * per_plane;
+    int chunk = (int)(rem / a.ninner);
+    int64_t inner = rem - (int64_t)chunk * a.ninner;
+    int64_t line = plane * a.ninner + inner;
+
+    int c0 = (int)a.chunk_ends[chunk], c1 = (int)a.chunk_ends[chunk + 1];
+    int p0 = c0 - a.maxw + 1; if (p0 < 0) p0 = 0;
+    int p1 = c1 + a.maxw - 1; if (p1 > a.n) p1 = a.n;
+    int m = p1 - p0;
+    const float *d = a.data + plane * a.outer_stride + inner + (int64_t)p0 * a.estride;
+    u8 *o = a.out + plane * a.outer_stride + inner + (int64_t)c0 * a.estride;
+    int64_t sbase = ((plane * a.nchunks + chunk) * (int64_t)(a.mpad + 1)) * a.ninner + inner;
+    double *cum = a.cum + sbase;
+    u8 *pn = a.pn + ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
+    const int64_t es = a.estride, ss = a.ninner;
+    float thr = a.thr[line * a.nchunks + chunk];
+
+    for (int i = 0; i < m; i++) pn[(int64_t)i * ss] = 0;
+    for (int wi = 0; wi < a.nwin; wi++) {
+        const int w = (int)a.windows[wi];
+        const double limit = (double)thr / a.tf[wi];
+        const double sc = (double)a.scale[wi];
+        const double nsc = (double)(-a.scale[wi]);
+        double c = 0.0;
+        cum[0] = 0.0;
+        int lastpos = -(1 << 30), lastneg = -(1 << 30);
+        for (int i = 0; i < m; i++) {
+            double x = (double)d[(int64_t)i * es];
+            u8 st = pn[(int64_t)i * ss];
+            if ((st & 1) && x > limit) x = limit;
+            else if ((st & 2) && x < -limit) x = -limit;
+            c = c + x;
+            cum[(int64_t)(i + 1) * ss] = c;
+            int j = i + 1 - w;
+            if (j >= 0) {
+                double avg = c - cum[(int64_t)j * ss];
+                if (avg * sc > limit) lastpos = j;
+                if (avg * nsc > limit) lastneg = j;
+                u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+                if (add) pn[(int64_t)j * ss] |= add;
+            }
+        }
+        int jt = m - w + 1; if (jt < 0) jt = 0;
+        for (int j = jt; j < m; j++) {
+            u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+            if (add) pn[(int64_t)j * ss] |= add;
+        }
+    }
+    int rel = c0 - p0;
+    for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = pn[(int64_t)(rel + i) * ss] ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------
+// S10 _combine_flags (flagging.py:784-816) + S11 _unaverage_freq (878-918)
+// ----------------------------------------------------------------------------
+// c1[t,fa] = any over the time window of (spec | time | freq); all (cp,T,Fa)
+__global__ void __launch_bounds__(256)
+k_combine_time(const u8 *__restrict__ spec, const u8 *__restrict__ time_f,
+               const u8 *__restrict__ freq_f, int64_t total, int T, int Fa, int lo, int ext,
+               u8 *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t row = i / Fa;
+    int f = (int)(i - row * Fa);
+    int64_t cp = row / T;
+    int t = (int)(row - cp * T);
+    if (spec[cp * Fa + f]) { out[i] = ext > 0 ? 1 : 0; return; }
+    int t0 = t + lo < 0 ? 0 : t + lo;
+    int t1 = t + lo + ext > T ? T : t + lo + ext;
+    u8 any = 0;
+    for (int tt = t0; tt < t1; tt++) {
+        int64_t k = (cp * T + tt) * (int64_t)Fa + f;
+        any |= (u8)(time_f[k] | freq_f[k]);
+    }
+    out[i] = any ? 1 : 0;
+}
+
+// d[t,f] = any over the frequency window of c1[t, f'/avg]; per-row and
+// per-column totals of d (the counts taken BEFORE the row extension,
+// flagging.py:902-911).  One block per (cp, t) row.
+__global__ void __launch_bounds__(256)
+k_unaverage_rows(const u8 *__restrict__ c1, int T, int Fa, int F, int lo, int ext, int avg,
+                 u8 *__restrict__ d, int *__restrict__ rowcnt, int *__restrict__ colcnt)
+{
+    __shared__ int s_cnt;
+    int64_t row = blockIdx.x;  // cp*T + t
+    int64_t cp = row / T;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const u8 *src = c1 + row * Fa;
+    int local = 0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        int f0 = f + lo < 0 ? 0 : f + lo;
+        int f1 = f + lo + ext > F ? F : f + lo + ext;
+        u8 any = 0;
+        for (int ff = f0; ff < f1; ff++) any |= src[ff / avg];
+        any = any ? 1 : 0;
+        d[row * F + f] = any;
+        if (any) { local++; atomicAdd(&colcnt[cp * F + f], 1); }
+    }
+    atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcnt[row] = s_cnt;
+}
+
+// out = d | row rule | column rule | isnan(input)   (flagging.py:910-918, 776-781)
+// optionally accumulates iter_flags |= out for the next major iteration
+__global__ void __launch_bounds__(256)
+k_finalize_flags(const u8 *__restrict__ d, const int *__restrict__ rowcnt,
+                 const int *__restrict__ colcnt, const void *__restrict__ vis, int vis_kind,
+                 int64_t total, int T, int F, double row_limit, double col_limit,
+                 u8 *__restrict__ out, u8 *__restrict__ iter_flags)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t row = i / F;
+    int f = (int)(i - row * F);
+    int64_t cp = row / T;
+    bool fl = d[i] != 0;
+    if ((double)rowcnt[row] > row_limit) fl = true;
+    if ((double)colcnt[cp * F + f] > col_limit) fl = true;
+    if (vis) {
+        if (vis_kind == TC_VIS_COMPLEX64) {
+            float2 v = ((const float2 *)vis)[i];
+            if (v.x != v.x || v.y != v.y) fl = true;
+        } else {
+            float v = ((const float *)vis)[i];
+            if (v != v) fl = true;
+        }
+    }
+    out[i] = fl ? 1 : 0;
+    if (iter_flags && fl) iter_flags[i] = 1;
+}
+
+// normalise arbitrary non-zero flag bytes to 0/1
+__global__ void __launch_bounds__(256)
+k_norm_flags(const u8 *__restrict__ in, u8 *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = in[i] ? 1 : 0;
+}

@@ -1,0 +1,330 @@
+// st_driver.cuh -- host-side sequencing of the SumThreshold stages on the
+// device (reference: _get_baseline_flags flagging.py:921-976, _get_flags_impl
+// 745-781, _get_background2d 516-579).
+//
+// Two layouts of every per-plane array are used: "TF" = (plane, time, chan)
+// and "FT" = (plane, chan, time).  Whatever walks the time axis sequentially
+// (time box passes, time SumThreshold scan) runs on TF with one thread per
+// channel; whatever walks the frequency axis (frequency box passes, frequency
+// SumThreshold scan, NaN interpolation) runs on FT with one thread per dump.
+// Either way a warp touches 32 consecutive addresses per step.  Frequency
+// chunks are contiguous in FT, which makes the per-chunk medians 1-D ranges.
+#pragma once
+#include "k_elementwise.cuh"
+#include "k_filter.cuh"
+#include "k_select.cuh"
+#include "k_sumthreshold.cuh"
+
+#define MAD_NORMAL 1.4826  // tricolour/flagging.py:22
+
+static int dev_upload_i64(tc_context *c, const int64_t *h, size_t n, int64_t **d)
+{
+    TC_TRY(tc_alloc(c, n, d));
+    TC_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    return TC_OK;
+}
+
+// contiguous FT ranges of every (plane, chunk)
+static int dev_make_ranges(tc_context *c, int64_t np, int64_t T, int64_t Fa, const int64_t *ce,
+                           int nce, int64_t **lo, int64_t **hi, int64_t *max_range)
+{
+    int nch = nce - 1;
+    std::vector<int64_t> hlo((size_t)np * nch), hhi((size_t)np * nch);
+    int64_t mr = 0;
+    for (int64_t p = 0; p < np; p++)
+        for (int k = 0; k < nch; k++) {
+            hlo[p * nch + k] = p * T * Fa + ce[k] * T;
+            hhi[p * nch + k] = p * T * Fa + ce[k + 1] * T;
+            if ((ce[k + 1] - ce[k]) * T > mr) mr = (ce[k + 1] - ce[k]) * T;
+        }
+    TC_TRY(dev_upload_i64(c, hlo.data(), hlo.size(), lo));
+    TC_TRY(dev_upload_i64(c, hhi.data(), hhi.size(), hi));
+    *max_range = mr;
+    return TC_OK;
+}
+
+struct BgWork {
+    u8 *fl_TF, *fl_FT;  // working copy of the flags (gets modified)
+    float *v_TF, *w_TF, *v_FT, *w_FT;
+};
+
+static int dev_bg_work_alloc(tc_context *c, int64_t N, bool need_tf, BgWork *w)
+{
+    TC_TRY(tc_alloc(c, N, &w->fl_FT));
+    w->fl_TF = nullptr; w->v_TF = w->w_TF = w->v_FT = w->w_FT = nullptr;
+    if (need_tf) {
+        TC_TRY(tc_alloc(c, N, &w->fl_TF));
+        TC_TRY(tc_alloc(c, N, &w->v_TF));
+        TC_TRY(tc_alloc(c, N, &w->w_TF));
+        TC_TRY(tc_alloc(c, N, &w->v_FT));
+        TC_TRY(tc_alloc(c, N, &w->w_FT));
+    }
+    return TC_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_abs_sub(const float *a, const float *b, float *out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fabsf(a[i] - b[i]);
+}
+
+// one masked_gaussian_filter (flagging.py:469-513) from (data, work flags) to
+// out_FT; resid != 0 stores |data - background| instead (flagging.py:561-566)
+static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const float *data_TF,
+                             const float *data_FT, BgWork &w, int64_t r0, int64_t r1, int resid,
+                             float *out_FT)
+{
+    int64_t N = np * (int64_t)T * Fa;
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    if (r0 > 0 && r1 > 0) {
+        a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
+        a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
+        a.data = data_TF; a.flags = w.fl_TF; a.vout = w.v_TF; a.wout = w.w_TF;
+        TC_TRY(launch_box_filter(c, a));
+        TC_TRY(launch_transpose<float>(c, w.v_TF, w.v_FT, np, T, Fa));
+        TC_TRY(launch_transpose<float>(c, w.w_TF, w.w_FT, np, T, Fa));
+        memset(&a, 0, sizeof(a));
+        a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
+        a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
+        a.data = w.v_FT; a.win = w.w_FT; a.vout = out_FT; a.data2 = data_FT;
+        TC_TRY(launch_box_filter(c, a));
+    } else if (r0 > 0) {
+        a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
+        a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
+        a.data = data_TF; a.flags = w.fl_TF; a.vout = w.v_TF;
+        TC_TRY(launch_box_filter(c, a));
+        TC_TRY(launch_transpose<float>(c, w.v_TF, out_FT, np, T, Fa));
+        if (resid) {
+            TC_LAUNCH_NOSYNC(k_abs_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, out_FT, out_FT, N);
+            c->launches++;
+        }
+    } else if (r1 > 0) {
+        a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
+        a.mode_in = FIN_MASKED; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
+        a.data = data_FT; a.flags = w.fl_FT; a.vout = out_FT; a.data2 = data_FT;
+        TC_TRY(launch_box_filter(c, a));
+    } else {
+        TC_LAUNCH_NOSYNC(k_masked_copy, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, w.fl_FT, N,
+                         resid ? FOUT_RESID : FOUT_BG, data_FT, out_FT);
+        c->launches++;
+    }
+    TC_KERNEL_CHECK();
+    return TC_OK;
+}
+
+// _get_background2d (flagging.py:516-579).  flags_* are the caller's flags
+// (not modified); the interpolated background lands in out_FT.
+static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const float *data_TF,
+                            const float *data_FT, const u8 *flags_TF, const u8 *flags_FT,
+                            int iterations, const int64_t *radii, double reject,
+                            const int64_t *range_lo, const int64_t *range_hi, int nchunks,
+                            int64_t max_range, float *out_FT)
+{
+    int64_t N = np * (int64_t)T * Fa;
+    bool need_tf = false;
+    for (int k = 0; k <= iterations; k++) if (radii[2 * k] > 0) need_tf = true;
+    if (T == 1) need_tf = false;
+    BgWork w;
+    tc_mark mark = tc_arena_mark(c);
+    TC_TRY(dev_bg_work_alloc(c, N, need_tf, &w));
+    TC_CUDA(cudaMemcpyAsync(w.fl_FT, flags_FT, N, cudaMemcpyDeviceToDevice, c->stream));
+    if (need_tf) TC_CUDA(cudaMemcpyAsync(w.fl_TF, flags_TF, N, cudaMemcpyDeviceToDevice, c->stream));
+    for (int it = 0; it <= iterations; it++) {
+        int64_t r0 = T == 1 ? 0 : radii[2 * it], r1 = radii[2 * it + 1];
+        bool final_pass = it == iterations;
+        TC_TRY(dev_masked_filter(c, np, T, Fa, data_TF, data_FT, w, r0, r1, final_pass ? 0 : 1, out_FT));
+        if (final_pass) break;
+        ChunkSelectArgs s;
+        memset(&s, 0, sizeof(s));
+        s.resid = out_FT; s.flags = w.fl_FT; s.range_lo = range_lo; s.range_hi = range_hi;
+        s.thr_mult = MAD_NORMAL * reject; s.mode = CS_BACKGROUND; s.take_abs = 0; s.medians = nullptr;
+        TC_TRY(launch_chunk_select(c, s, np * nchunks, max_range));
+        // the next time-axis filter reads the flags in TF
+        bool next_tf = need_tf && radii[2 * (it + 1)] > 0;
+        if (next_tf) TC_TRY(launch_transpose<u8>(c, w.fl_FT, w.fl_TF, np, Fa, T));
+    }
+    // _linearly_interpolate_nans along frequency for every (plane, dump)
+    TC_LAUNCH_NOSYNC(k_interp_nans, tc_blocks_for(np * T, 128), 128, 0, c->stream, out_FT, np * (int64_t)T,
+                     (int64_t)T, (int64_t)T * Fa, (int64_t)1, Fa, (int64_t)T);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    tc_arena_release(c, mark);
+    return TC_OK;
+}
+
+// _sum_threshold (flagging.py:684-742) for np planes.
+// axis 0: scans time (TF layout for the scan, FT for the medians)
+// axis 1: scans frequency (FT for the scan, TF for the medians)
+// chunk_ends (host, nce entries) partition the scanned axis.
+static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis, const float *d_TF,
+                             const float *d_FT, const u8 *fl_TF, const u8 *fl_FT,
+                             const u8 *fl2_TF, const int64_t *windows, const double *tf,
+                             const float *scale, int nwin, double nsigma, const int64_t *ce,
+                             int nce, u8 *out /* TF for axis 0, FT for axis 1 */)
+{
+    TC_REQUIRE(nwin > 0, "zero-size array to reduction operation maximum which has no identity");
+    TC_REQUIRE(nwin <= TC_MAX_WINDOWS, "at most %d SumThreshold windows are supported", TC_MAX_WINDOWS);
+    int n = axis == 0 ? T : Fa;
+    int nchunks = nce - 1;
+    int64_t maxw = 0;
+    for (int k = 0; k < nwin; k++) {
+        TC_REQUIRE(windows[k] >= 1, "unable to broadcast argument 1 to output array (window %lld < 1)",
+                   (long long)windows[k]);
+        if (windows[k] > maxw) maxw = windows[k];
+    }
+    int maxlen = 0, mpad = 0;
+    for (int k = 0; k < nchunks; k++) {
+        TC_REQUIRE(ce[k + 1] >= ce[k] && ce[k] >= 0 && ce[k + 1] <= n, "bad chunk boundaries");
+        int len = (int)(ce[k + 1] - ce[k]);
+        if (len > maxlen) maxlen = len;
+        int64_t p0 = ce[k] - maxw + 1; if (p0 < 0) p0 = 0;
+        int64_t p1 = ce[k + 1] + maxw - 1; if (p1 > n) p1 = n;
+        if ((int)(p1 - p0) > mpad) mpad = (int)(p1 - p0);
+    }
+    if (nchunks <= 0 || np == 0) return TC_OK;
+    tc_mark mark = tc_arena_mark(c);
+    int64_t *d_ce = nullptr;
+    TC_TRY(dev_upload_i64(c, ce, (size_t)nce, &d_ce));
+    int64_t ninner = axis == 0 ? Fa : T;  // lines per plane
+    int64_t nlines = np * ninner;
+    float *thr = nullptr;
+    TC_TRY(tc_alloc(c, (size_t)nlines * nchunks, &thr));
+    LineMedianArgs m;
+    memset(&m, 0, sizeof(m));
+    m.nlines = nlines; m.ninner = ninner; m.outer_stride = (int64_t)T * Fa;
+    m.elem_stride = 1; m.mode = LM_ST_THRESHOLD; m.use_abs = 1;
+    m.thr_scale = nsigma * MAD_NORMAL; m.out = thr;
+    if (axis == 0) {  // a time line of channel f is contiguous in FT
+        m.data = d_FT; m.flags = fl_FT; m.flags2 = nullptr; m.inner_stride = T;
+    } else {          // a frequency line of dump t is contiguous in TF
+        m.data = d_TF; m.flags = fl_TF; m.flags2 = fl2_TF; m.inner_stride = Fa;
+    }
+    m.seg_ends = d_ce; m.nseg = nchunks; m.n = n;
+    TC_TRY(launch_line_median(c, m, maxlen));
+
+    StScanArgs s;
+    memset(&s, 0, sizeof(s));
+    s.data = axis == 0 ? d_TF : d_FT;
+    s.thr = thr; s.out = out; s.nlines = nlines; s.ninner = ninner;
+    s.outer_stride = (int64_t)T * Fa; s.estride = ninner; s.n = n; s.nchunks = nchunks;
+    s.chunk_ends = d_ce; s.nwin = nwin; s.maxw = (int)maxw; s.mpad = mpad;
+    for (int k = 0; k < nwin; k++) { s.windows[k] = windows[k]; s.tf[k] = tf[k]; s.scale[k] = scale[k]; }
+    TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad + 1) * ninner, &s.cum));
+    TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn));
+    TC_LAUNCH_NOSYNC(k_st_scan, tc_blocks_for(nlines * nchunks, 128), 128, 0, c->stream, s);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    tc_arena_release(c, mark);
+    return TC_OK;
+}
+
+// ----------------------------------------------------------------------------
+// one _get_flags_impl pass over np planes
+// ----------------------------------------------------------------------------
+static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *vis, int vis_kind,
+                              const u8 *in_flags, int64_t np, int T, int F, u8 *out_flags,
+                              u8 *iter_flags_accum)
+{
+    const int avg = (int)p->average_freq;
+    const int Fa = (F + avg - 1) / avg;
+    const int64_t N = np * (int64_t)T * Fa;
+    const int64_t NF = np * (int64_t)T * F;
+    const int nce = p->nchunk_ends, nchunks = nce - 1;
+    const int iters = p->background_iterations;
+    TC_REQUIRE(nchunks >= 0, "freq_chunk_ends must not be empty");
+    tc_mark pass_mark = tc_arena_mark(c);
+
+    float *data_TF, *data_FT;
+    u8 *fl_TF, *fl_FT;
+    TC_TRY(tc_alloc(c, N, &data_TF)); TC_TRY(tc_alloc(c, N, &data_FT));
+    TC_TRY(tc_alloc(c, N, &fl_TF)); TC_TRY(tc_alloc(c, N, &fl_FT));
+    // S1 _average_freq
+    TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
+                     data_TF, fl_TF);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    TC_TRY(launch_transpose<float>(c, data_TF, data_FT, np, T, Fa));
+    TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+
+    // S2 _time_median -> (np, Fa)
+    float *spec_data, *spec_bg;
+    u8 *spec_fl, *spec_out;
+    TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_data)); TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_bg));
+    TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_fl)); TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_out));
+    {
+        LineMedianArgs m;
+        memset(&m, 0, sizeof(m));
+        m.data = data_FT; m.flags = fl_FT; m.nlines = np * Fa; m.ninner = Fa;
+        m.outer_stride = (int64_t)T * Fa; m.inner_stride = T; m.elem_stride = 1; m.n = T;
+        m.mode = LM_TIME_MEDIAN; m.use_abs = 0; m.out = spec_data; m.out_flags = spec_fl;
+        TC_TRY(launch_line_median(c, m, T));
+    }
+    // spectrum background (flagging.py:945-949) and its SumThreshold (950-952)
+    int64_t *slo, *shi, smax;
+    TC_TRY(dev_make_ranges(c, np, 1, Fa, p->freq_chunk_ends, nce, &slo, &shi, &smax));
+    TC_TRY(dev_background2d(c, np, 1, Fa, spec_data, spec_data, spec_fl, spec_fl, iters, p->radii_spec,
+                            p->background_reject, slo, shi, nchunks, smax, spec_bg));
+    TC_LAUNCH_NOSYNC(k_sub, tc_blocks_for(np * Fa, 256), 256, 0, c->stream, spec_data, spec_bg, spec_data,
+                     np * (int64_t)Fa);
+    c->launches++;
+    TC_TRY(dev_sum_threshold(c, np, 1, Fa, 1, spec_data, spec_data, spec_fl, spec_fl, nullptr,
+                             p->windows_freq, p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
+                             p->freq_chunk_ends, nce, spec_out));
+    // flags |= spec_flags (flagging.py:954), both layouts
+    TC_LAUNCH_NOSYNC(k_or_spec, tc_blocks_for(N, 256), 256, 0, c->stream, fl_TF, spec_out, N, T, Fa);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+
+    // 2-D background (flagging.py:957-961)
+    float *bg_FT, *dres_TF;
+    TC_TRY(tc_alloc(c, N, &bg_FT)); TC_TRY(tc_alloc(c, N, &dres_TF));
+    int64_t *rlo, *rhi, rmax;
+    TC_TRY(dev_make_ranges(c, np, T, Fa, p->freq_chunk_ends, nce, &rlo, &rhi, &rmax));
+    TC_TRY(dev_background2d(c, np, T, Fa, data_TF, data_FT, fl_TF, fl_FT, iters, p->radii_2d,
+                            p->background_reject, rlo, rhi, nchunks, rmax, bg_FT));
+    // data -= background (flagging.py:962), in both layouts
+    TC_LAUNCH_NOSYNC(k_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, bg_FT, bg_FT, N);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    float *dres_FT = bg_FT;
+    TC_TRY(launch_transpose<float>(c, dres_FT, dres_TF, np, Fa, T));
+
+    // SumThreshold along time (flagging.py:964-965)
+    u8 *time_TF, *freq_FT, *freq_TF;
+    TC_TRY(tc_alloc(c, N, &time_TF)); TC_TRY(tc_alloc(c, N, &freq_FT)); TC_TRY(tc_alloc(c, N, &freq_TF));
+    int64_t tce[2] = {0, T};
+    TC_TRY(dev_sum_threshold(c, np, T, Fa, 0, dres_TF, dres_FT, fl_TF, fl_FT, nullptr, p->windows_time,
+                             p->tf_time, p->scale_time, p->nwin_time, p->outlier_nsigma, tce, 2, time_TF));
+    // flags |= time_flags; SumThreshold along frequency (flagging.py:967-969)
+    TC_TRY(dev_sum_threshold(c, np, T, Fa, 1, dres_TF, dres_FT, fl_TF, fl_FT, time_TF, p->windows_freq,
+                             p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
+                             p->freq_chunk_ends, nce, freq_FT));
+    TC_TRY(launch_transpose<u8>(c, freq_FT, freq_TF, np, Fa, T));
+
+    // _combine_flags + _unaverage_freq + final isnan OR
+    u8 *c1 = fl_FT;  // fl_FT is no longer needed
+    int te = (int)p->time_extend, fe = (int)p->freq_extend;
+    TC_LAUNCH_NOSYNC(k_combine_time, tc_blocks_for(N, 256), 256, 0, c->stream, spec_out, time_TF, freq_TF, N, T,
+                     Fa, -(te / 2), te, c1);
+    c->launches++;
+    u8 *dflags;
+    int *rowcnt, *colcnt;
+    TC_TRY(tc_alloc(c, NF, &dflags));
+    TC_TRY(tc_alloc(c, np * (int64_t)T, &rowcnt));
+    TC_TRY(tc_alloc(c, np * (int64_t)F, &colcnt));
+    TC_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * np * (size_t)F, c->stream));
+    TC_LAUNCH(k_unaverage_rows, (unsigned)(np * T), 256, 0, c->stream, c1, T, Fa, F, -(fe / 2), fe, avg, dflags,
+              rowcnt, colcnt);
+    c->launches++;
+    TC_LAUNCH_NOSYNC(k_finalize_flags, tc_blocks_for(NF, 256), 256, 0, c->stream, dflags, rowcnt, colcnt, vis,
+                     vis_kind, NF, T, F, p->flag_all_freq_frac * (double)F, (double)T * p->flag_all_time_frac,
+                     out_flags, iter_flags_accum);
+    c->launches++;
+    TC_KERNEL_CHECK();
+    tc_arena_release(c, pass_mark);
+    return TC_OK;
+}

@@ -1,0 +1,156 @@
+// tc_common.cuh -- context, workspace arena and error plumbing.
+#pragma once
+#include "tc_rt.h"
+#include "../../include/tricolour_b200.h"
+
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <string>
+
+typedef uint8_t u8;
+
+// ---------------------------------------------------------------- errors ----
+static thread_local char g_tc_err[512] = "";
+
+static int tc_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_tc_err, sizeof(g_tc_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TC_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess)                                                     \
+            return tc_fail(TC_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);            \
+    } while (0)
+
+#define TC_TRY(call)                 \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != TC_OK) return rc_; \
+    } while (0)
+
+#define TC_KERNEL_CHECK() TC_CUDA(cudaGetLastError())
+
+#define TC_REQUIRE(cond, ...)                                   \
+    do {                                                        \
+        if (!(cond)) return tc_fail(TC_ERR_VALUE, __VA_ARGS__); \
+    } while (0)
+
+// --------------------------------------------------------------- context ----
+struct tc_block { char *ptr; size_t size; };
+
+struct tc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int smem_optin = 227 * 1024;
+    std::vector<tc_block> blocks;  // arena blocks; blocks[0] is the main one
+    size_t cur_block = 0, cur_off = 0;
+    size_t used_total = 0;         // bytes handed out since the last reset
+    size_t peak = 0;
+    unsigned long long launches = 0;  // kernels launched through this context
+};
+
+static inline size_t tc_align(size_t n, size_t a = 256) { return (n + a - 1) / a * a; }
+
+// start of an API call: if the previous call overflowed into extra blocks,
+// fold everything into one block of the peak size.
+static int tc_arena_reset(tc_context *c)
+{
+    if (c->blocks.size() > 1) {
+        TC_CUDA(cudaStreamSynchronize(c->stream));
+        for (auto &b : c->blocks) cudaFree(b.ptr);
+        c->blocks.clear();
+        size_t want = tc_align(c->peak + (c->peak >> 3), 1 << 20);
+        char *p = nullptr;
+        TC_CUDA(cudaMalloc((void **)&p, want));
+        c->blocks.push_back({p, want});
+    }
+    c->cur_block = 0;
+    c->cur_off = 0;
+    c->used_total = 0;
+    return TC_OK;
+}
+
+static int tc_arena_alloc(tc_context *c, size_t bytes, void **out)
+{
+    bytes = tc_align(bytes ? bytes : 1);
+    while (true) {
+        if (c->cur_block < c->blocks.size()) {
+            tc_block &b = c->blocks[c->cur_block];
+            if (c->cur_off + bytes <= b.size) {
+                *out = b.ptr + c->cur_off;
+                c->cur_off += bytes;
+                c->used_total += bytes;
+                if (c->used_total > c->peak) c->peak = c->used_total;
+                return TC_OK;
+            }
+            c->cur_block++;
+            c->cur_off = 0;
+            continue;
+        }
+        size_t want = tc_align(bytes > (size_t)(64 << 20) ? bytes : (size_t)(64 << 20), 1 << 20);
+        char *p = nullptr;
+        cudaError_t e = cudaMalloc((void **)&p, want);
+        if (e != cudaSuccess)
+            return tc_fail(TC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        c->blocks.push_back({p, want});
+    }
+}
+
+// stack discipline inside one API call: everything allocated after a mark is
+// handed back by the matching release (stream order makes the reuse safe)
+struct tc_mark { size_t block, off, used; };
+static inline tc_mark tc_arena_mark(tc_context *c) { return tc_mark{c->cur_block, c->cur_off, c->used_total}; }
+static inline void tc_arena_release(tc_context *c, tc_mark m)
+{
+    c->cur_block = m.block; c->cur_off = m.off; c->used_total = m.used;
+}
+
+template <typename T> static int tc_alloc(tc_context *c, size_t count, T **out)
+{
+    void *p = nullptr;
+    TC_TRY(tc_arena_alloc(c, count * sizeof(T), &p));
+    *out = (T *)p;
+    return TC_OK;
+}
+
+// Stage a host or device array on the device.  space == TC_HOST copies through
+// the context stream; TC_DEVICE uses the pointer as is.
+template <typename T>
+static int tc_stage_in(tc_context *c, const T *src, size_t count, int space, const T **dev)
+{
+    if (space == TC_DEVICE) { *dev = src; return TC_OK; }
+    T *d = nullptr;
+    TC_TRY(tc_alloc(c, count, &d));
+    if (count) TC_CUDA(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dev = d;
+    return TC_OK;
+}
+
+template <typename T>
+static int tc_stage_out_begin(tc_context *c, T *dst, size_t count, int space, T **dev)
+{
+    if (space == TC_DEVICE) { *dev = dst; return TC_OK; }
+    return tc_alloc(c, count, dev);
+}
+
+template <typename T>
+static int tc_stage_out_end(tc_context *c, T *dst, const T *dev, size_t count, int space)
+{
+    if (space == TC_DEVICE) return TC_OK;
+    if (count) TC_CUDA(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    TC_CUDA(cudaStreamSynchronize(c->stream));
+    return TC_OK;
+}
+
+static inline unsigned tc_blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

@@ -1,0 +1,122 @@
+# -*- coding: utf-8 -*-
+"""
+Strategy execution with device-resident windows (reference:
+tricolour/apps/tricolour/strat_executor.py:29-83 and the YAML schema of
+tricolour/conf/default.yaml).
+
+The reference chains dask arrays, so every task moves the whole block through
+host memory.  Here a block is uploaded once, all tasks run on the GPU against
+the resident visibilities and flags with the reference's combine rule per task
+(OR / replace), and only the final flags come back.
+"""
+import numpy as np
+
+from . import _cabi
+from ._cabi import check, ptr
+from .flagging import (sum_threshold_flagger, uvcontsub_flagger, flag_autos,
+                       flag_nans_and_zeros, apply_static_mask)
+
+
+def load_strategies(path):
+    """``strategies:`` list of a tricolour YAML file (app.py:101-120)."""
+    import yaml
+    with open(path) as f:
+        return yaml.safe_load(f)["strategies"]
+
+
+def _flags_or(a, b):
+    """device flags a | b through the library (strat_executor.py:43, 54, 59, 76)"""
+    import torch
+    au8 = a.view(torch.uint8) if a.dtype == torch.bool else a
+    bu8 = b.view(torch.uint8) if b.dtype == torch.bool else b
+    out = torch.empty_like(au8)
+    dev = a.device.index if a.device.index is not None else torch.cuda.current_device()
+    ctx = _cabi.get_context(dev, torch.cuda.current_stream(dev).cuda_stream)
+    check(_cabi.load().tc_flags_or(ctx.handle, ptr(au8.contiguous()), ptr(bu8.contiguous()),
+                                   ptr(out), int(out.numel()), _cabi.DEVICE))
+    return out.view(torch.bool) if a.dtype == torch.bool else out
+
+
+class StrategyExecutor(object):
+    """Same constructor and ``apply_strategies`` contract as the reference's
+    executor; ``flag_windows`` / ``vis_windows`` are numpy arrays (uploaded
+    once) or torch CUDA tensors (used in place)."""
+
+    def __init__(self, antenna_positions, unique_baselines,
+                 chan_freq, chan_width, masked_channels, strategies):
+        self.ant_pos = antenna_positions
+        self.ubl = unique_baselines
+        self.chan_freq = chan_freq
+        self.chan_width = chan_width
+        self.masked_channels = masked_channels
+        self.strategies = strategies
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, etype, evalue, etraceback):
+        pass
+
+    def apply_strategies(self, flag_windows, vis_windows, device=None):
+        import torch
+        host_io = not _cabi.is_device_array(flag_windows)
+        if host_io:
+            if not torch.cuda.is_available():
+                raise RuntimeError("tricolour_b200: no CUDA device available; there is no CPU fallback")
+            dev = torch.device("cuda", _cabi.default_device() if device is None else int(device))
+            f_np = np.ascontiguousarray(flag_windows)
+            fdt = f_np.dtype
+            f8 = f_np.view(np.uint8) if f_np.dtype.itemsize == 1 else (f_np != 0).view(np.uint8)
+            v_np = np.ascontiguousarray(vis_windows, dtype=np.complex64)
+            with torch.cuda.device(dev):
+                flags = torch.from_numpy(f8).to(dev, non_blocking=True).view(torch.bool)
+                vis = torch.from_numpy(v_np).to(dev, non_blocking=True)
+        else:
+            dev = flag_windows.device
+            flags, vis = flag_windows, vis_windows
+            fdt = None
+            if flags.dtype != torch.bool:
+                flags = flags != 0
+        with torch.cuda.device(dev):
+            flags = self._run(flags, vis)
+            if not host_io:
+                return flags if flag_windows.dtype == torch.bool else flags.to(flag_windows.dtype)
+            out = flags.view(torch.uint8).cpu().numpy()
+        return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
+
+    def _run(self, flag_windows, vis_windows):
+        original = flag_windows.clone()
+        ubl = np.asarray(self.ubl)
+        for strategy in self.strategies:
+            try:
+                task = strategy['task']
+            except KeyError:
+                raise ValueError("strategy has no 'task': %s" % strategy)
+            kwargs = strategy.get('kwargs', {}) or {}
+            if task == "sum_threshold":
+                new_flags = sum_threshold_flagger(vis_windows, flag_windows, **kwargs)
+                # sum threshold builds upon any flags that came previous
+                flag_windows = _flags_or(new_flags, flag_windows)
+            elif task == "uvcontsub_flagger":
+                # discards previous flags per its or_original_from_cycle rule
+                flag_windows = uvcontsub_flagger(vis_windows, flag_windows, **kwargs)
+            elif task == "flag_autos":
+                new_flags = flag_autos(flag_windows, [ubl])
+                flag_windows = _flags_or(new_flags, flag_windows)
+            elif task == "combine_with_input_flags":
+                flag_windows = _flags_or(flag_windows, original)
+            elif task == "unflag":
+                flag_windows = flag_windows.new_zeros(flag_windows.shape)
+            elif task == "flag_nans_zeros":
+                flag_windows = flag_nans_and_zeros(vis_windows, flag_windows)
+            elif task == "apply_static_mask":
+                new_flags = apply_static_mask(flag_windows, ubl, self.ant_pos,
+                                              self.masked_channels, self.chan_freq,
+                                              self.chan_width, **kwargs)
+                if kwargs["accumulation_mode"].strip() == "or":
+                    flag_windows = _flags_or(new_flags, flag_windows)
+                else:
+                    flag_windows = new_flags
+            else:
+                raise ValueError("Task '%s' does not name a valid task", task)
+        return flag_windows

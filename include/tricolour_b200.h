@@ -54,6 +54,14 @@ void tc_context_destroy(tc_context *ctx);
 int tc_synchronize(tc_context *ctx);
 /* number of kernels this context has launched so far */
 unsigned long long tc_launch_count(tc_context *ctx);
+/* Optional timing of the kernel families with CUDA events on the context's
+ * stream (used by bench.py for the roofline of the dominant kernel).
+ * tc_profile_read synchronises on the recorded events. */
+int tc_profile_enable(tc_context *ctx, int on);
+int tc_profile_reset(tc_context *ctx);
+int tc_profile_count(void);
+const char *tc_profile_name(int id);
+int tc_profile_read(tc_context *ctx, int id, double *total_ms, long long *launches);
 /* workspace high-water mark in bytes */
 size_t tc_workspace_peak(tc_context *ctx);
 int tc_alloc_pinned(size_t nbytes, void **out);

@@ -64,6 +64,11 @@ _SIGNATURES = {
     "tc_synchronize": (_int, [_vp]),
     "tc_launch_count": (ctypes.c_ulonglong, [_vp]),
     "tc_workspace_peak": (ctypes.c_size_t, [_vp]),
+    "tc_profile_enable": (_int, [_vp, _int]),
+    "tc_profile_reset": (_int, [_vp]),
+    "tc_profile_count": (_int, []),
+    "tc_profile_name": (ctypes.c_char_p, [_int]),
+    "tc_profile_read": (_int, [_vp, _int, ctypes.POINTER(_dbl), ctypes.POINTER(ctypes.c_longlong)]),
     "tc_alloc_pinned": (_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "tc_free_pinned": (_int, [_vp]),
     "tc_is_emulated": (_int, []),
@@ -169,6 +174,22 @@ class Context(object):
 
     def workspace_peak(self):
         return int(load().tc_workspace_peak(self._h))
+
+    def profile(self, on=True):
+        check(load().tc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        check(load().tc_profile_reset(self._h))
+
+    def profile_read(self):
+        """{kernel family: (total_ms, launches)} measured with CUDA events"""
+        lib = load()
+        out = {}
+        for i in range(lib.tc_profile_count()):
+            ms, n = _dbl(0), ctypes.c_longlong(0)
+            check(lib.tc_profile_read(self._h, i, ctypes.byref(ms), ctypes.byref(n)))
+            out[lib.tc_profile_name(i).decode()] = (ms.value, n.value)
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

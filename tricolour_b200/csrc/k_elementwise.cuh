@@ -271,8 +271,10 @@ static int launch_transpose(tc_context *c, const T *in, T *out, int64_t nplanes,
     for (int64_t p0 = 0; p0 < nplanes; p0 += 65535) {
         int64_t np = nplanes - p0 < 65535 ? nplanes - p0 : 65535;
         dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)np);
+        tc_prof_begin(c, TCP_TRANSPOSE);
         TC_LAUNCH(k_transpose<T>, grid, dim3(32, 8, 1), 0, c->stream, in + p0 * R * C,
                   out + p0 * R * C, R, C);
+        tc_prof_end(c);
         c->launches++;
     }
     TC_KERNEL_CHECK();

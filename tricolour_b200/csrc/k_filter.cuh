@@ -173,6 +173,7 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
 {
     if (a.nlines == 0 || a.n == 0) return TC_OK;
     a.div = tc_f32_pow4(2 * (int64_t)a.r + 1);
+    tc_prof_begin(c, TCP_BOX_FILTER);
     const size_t per_thread = (size_t)6 * 2 * a.r * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;
     int bd = (int)(smem_cap / per_thread);
@@ -199,6 +200,7 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
         a.gring_stride = threads;
         TC_LAUNCH_NOSYNC(k_box_filter<false>, (unsigned)blocks, bd2, 0, c->stream, a);
     }
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     return TC_OK;

@@ -232,11 +232,13 @@ static int launch_line_median(tc_context *c, const LineMedianArgs &a, int maxlen
     int64_t nwarps = a.nlines * nseg;
     if (nwarps == 0) return TC_OK;
     unsigned grid = tc_blocks_for(nwarps * 32, 128);
+    tc_prof_begin(c, TCP_LINE_MEDIAN);
     if (maxlen <= 128) TC_LAUNCH(k_line_median<4>, grid, 128, 0, c->stream, a);
     else if (maxlen <= 256) TC_LAUNCH(k_line_median<8>, grid, 128, 0, c->stream, a);
     else if (maxlen <= 512) TC_LAUNCH(k_line_median<16>, grid, 128, 0, c->stream, a);
     else if (maxlen <= 1024) TC_LAUNCH(k_line_median<32>, grid, 128, 0, c->stream, a);
     else TC_LAUNCH(k_line_median_long, grid, 128, 0, c->stream, a);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     return TC_OK;
@@ -386,7 +388,9 @@ static int launch_chunk_select(tc_context *c, const ChunkSelectArgs &a, int64_t 
     if (max_range <= 4096) bd = 128;
     else if (max_range <= 32768) bd = 256;
     else if (max_range <= 131072) bd = 512;
+    tc_prof_begin(c, TCP_CHUNK_SELECT);
     TC_LAUNCH(k_chunk_select, (unsigned)nranges, bd, 0, c->stream, a);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     return TC_OK;

@@ -147,8 +147,10 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
         if (next_tf) TC_TRY(launch_transpose<u8>(c, w.fl_FT, w.fl_TF, np, Fa, T));
     }
     // _linearly_interpolate_nans along frequency for every (plane, dump)
+    tc_prof_begin(c, TCP_INTERP);
     TC_LAUNCH_NOSYNC(k_interp_nans, tc_blocks_for(np * T, 128), 128, 0, c->stream, out_FT, np * (int64_t)T,
                      (int64_t)T, (int64_t)T * Fa, (int64_t)1, Fa, (int64_t)T);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     tc_arena_release(c, mark);
@@ -214,7 +216,9 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     for (int k = 0; k < nwin; k++) { s.windows[k] = windows[k]; s.tf[k] = tf[k]; s.scale[k] = scale[k]; }
     TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad + 1) * ninner, &s.cum));
     TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn));
+    tc_prof_begin(c, TCP_ST_SCAN);
     TC_LAUNCH_NOSYNC(k_st_scan, tc_blocks_for(nlines * nchunks, 128), 128, 0, c->stream, s);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     tc_arena_release(c, mark);
@@ -242,8 +246,10 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_TRY(tc_alloc(c, N, &data_TF)); TC_TRY(tc_alloc(c, N, &data_FT));
     TC_TRY(tc_alloc(c, N, &fl_TF)); TC_TRY(tc_alloc(c, N, &fl_FT));
     // S1 _average_freq
+    tc_prof_begin(c, TCP_PREP);
     TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
                      data_TF, fl_TF);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     TC_TRY(launch_transpose<float>(c, data_TF, data_FT, np, T, Fa));
@@ -308,6 +314,7 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     // _combine_flags + _unaverage_freq + final isnan OR
     u8 *c1 = fl_FT;  // fl_FT is no longer needed
     int te = (int)p->time_extend, fe = (int)p->freq_extend;
+    tc_prof_begin(c, TCP_COMBINE);
     TC_LAUNCH_NOSYNC(k_combine_time, tc_blocks_for(N, 256), 256, 0, c->stream, spec_out, time_TF, freq_TF, N, T,
                      Fa, -(te / 2), te, c1);
     c->launches++;
@@ -323,6 +330,7 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_LAUNCH_NOSYNC(k_finalize_flags, tc_blocks_for(NF, 256), 256, 0, c->stream, dflags, rowcnt, colcnt, vis,
                      vis_kind, NF, T, F, p->flag_all_freq_frac * (double)F, (double)T * p->flag_all_time_frac,
                      out_flags, iter_flags_accum);
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     tc_arena_release(c, pass_mark);

@@ -58,7 +58,58 @@ struct tc_context {
     size_t used_total = 0;         // bytes handed out since the last reset
     size_t peak = 0;
     unsigned long long launches = 0;  // kernels launched through this context
+    // optional per-kernel-family timing with CUDA events (tc_profile_*)
+    bool prof = false;
+    struct ProfRec { int id; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    double prof_ms[32] = {0};
+    long long prof_cnt[32] = {0};
 };
+
+enum { TCP_BOX_FILTER = 0, TCP_CHUNK_SELECT, TCP_LINE_MEDIAN, TCP_ST_SCAN, TCP_TRANSPOSE, TCP_PREP,
+       TCP_COMBINE, TCP_INTERP, TCP_ELEMENTWISE, TCP_UVCONTSUB, TCP_PACK, TCP_STATS, TCP_NIDS };
+static const char *const tc_prof_names[TCP_NIDS] = {
+    "box_filter", "chunk_select", "line_median", "st_scan", "transpose", "prep", "combine", "interp_nans",
+    "elementwise", "uvcontsub", "pack_unpack", "window_counts"};
+
+static inline void tc_prof_begin(tc_context *c, int id)
+{
+#ifndef TC_EMU
+    if (!c->prof) return;
+    tc_context::ProfRec r;
+    r.id = id;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, c->stream);
+    c->prof_recs.push_back(r);
+#else
+    (void)c; (void)id;
+#endif
+}
+static inline void tc_prof_end(tc_context *c)
+{
+#ifndef TC_EMU
+    if (!c->prof || c->prof_recs.empty()) return;
+    cudaEventRecord(c->prof_recs.back().b, c->stream);
+#else
+    (void)c;
+#endif
+}
+static inline void tc_prof_collect(tc_context *c)
+{
+#ifndef TC_EMU
+    for (auto &r : c->prof_recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.id] += ms; c->prof_cnt[r.id]++; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->prof_recs.clear();
+#else
+    (void)c;
+#endif
+}
 
 static inline size_t tc_align(size_t n, size_t a = 256) { return (n + a - 1) / a * a; }
 

@@ -71,6 +71,29 @@ int tc_synchronize(tc_context *c)
 }
 
 unsigned long long tc_launch_count(tc_context *c) { return c->launches; }
+
+int tc_profile_enable(tc_context *c, int on)
+{
+    tc_prof_collect(c);
+    c->prof = on != 0;
+    return TC_OK;
+}
+int tc_profile_reset(tc_context *c)
+{
+    tc_prof_collect(c);
+    for (int i = 0; i < TCP_NIDS; i++) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    return TC_OK;
+}
+int tc_profile_count(void) { return TCP_NIDS; }
+const char *tc_profile_name(int id) { return id >= 0 && id < TCP_NIDS ? tc_prof_names[id] : ""; }
+int tc_profile_read(tc_context *c, int id, double *ms, long long *count)
+{
+    TC_REQUIRE(id >= 0 && id < TCP_NIDS, "bad profile id");
+    tc_prof_collect(c);
+    *ms = c->prof_ms[id];
+    *count = c->prof_cnt[id];
+    return TC_OK;
+}
 size_t tc_workspace_peak(tc_context *c) { return c->peak; }
 
 int tc_alloc_pinned(size_t nbytes, void **out)
@@ -265,12 +288,14 @@ int tc_uvcontsub(tc_context *c, const void *vis, const uint8_t *flags, int64_t n
     TC_LAUNCH_NOSYNC(k_uv_twiddle, tc_blocks_for(F, 256), 256, 0, c->stream, tw, (int)F);
     c->launches++;
     for (int mi = 0; mi < major_cycles; mi++) {
+        tc_prof_begin(c, TCP_UVCONTSUB);
         TC_CUDA(cudaMemsetAsync(unfl, 0, sizeof(int) * (size_t)ncp, c->stream));
         TC_LAUNCH(k_uv_mean, dim3(tc_blocks_for(F, 256), (unsigned)ncp), 256, 0, c->stream, dvis, dout, (int)T,
                   (int)F, avg, unfl);
         TC_LAUNCH(k_uv_smooth, (unsigned)ncp, 256, 0, c->stream, avg, tw, (int)F, K, smooth);
         TC_LAUNCH_NOSYNC(k_uv_absres, tc_blocks_for(total, 256), 256, 0, c->stream, dvis, smooth, total, (int)T,
                          (int)F, absres);
+        tc_prof_end(c);
         c->launches += 3;
         ChunkSelectArgs s;
         memset(&s, 0, sizeof(s));

@@ -1,0 +1,94 @@
+# -*- coding: utf-8 -*-
+"""Host-side logic of the drop-in layer (no kernels involved)."""
+import numpy as np
+import pytest
+
+import oracle
+import tricolour_b200 as tb
+from tricolour_b200 import flagging as G, packing as P
+from tricolour_b200.util import casa_style_range
+import common
+
+
+def test_casa_style_range():
+    assert casa_style_range("") == (0, np.inf)
+    assert casa_style_range(" * ") == (0, np.inf)
+    assert casa_style_range("0~550") == [0.0, 550.0]
+    assert casa_style_range("1.5e2~2e3m") == [150.0, 2000.0]
+    for bad in ("abc", "1~", "~2", "1-2"):
+        with pytest.raises(ValueError):
+            casa_style_range(bad)
+    with pytest.raises(ValueError):
+        casa_style_range(3)
+
+
+def test_as_min_dtype_and_radii():
+    assert G._as_min_dtype(3).dtype == np.uint8
+    assert G._as_min_dtype(300).dtype == np.uint16
+    assert G._as_min_dtype(70000).dtype == np.uint32
+    assert G._as_min_dtype(-1).dtype == np.int64
+    # SURVEY.md section 7 table
+    for sig, r in (((62.5, 50), (54, 43)), ((12.5, 10), (10, 8)), ((32.5, 320), (28, 277)),
+                   ((6.5, 64), (5, 55)), ((10, 50), (8, 43)), ((2, 10), (1, 8))):
+        assert tuple(G._box_radii(sig)) == r
+    rad = G._background_radii(5, (12.5, 10.0))
+    assert rad.shape == (6, 2) and tuple(rad[0]) == (54, 43) and tuple(rad[-1]) == tuple(rad[-2]) == (10, 8)
+    assert np.array_equal(rad, oracle.background_radii(5, (12.5, 10.0)))
+
+
+def test_plan_matches_reference_conditioning():
+    plan = G._StPlan(10, [1, 2, 4, 8], [32, 48, 64, 128], 2.0, 5, 6.5, 64.0, G._as_min_dtype(3),
+                     G._as_min_dtype(3), np.linspace(0, 4096, 11).astype(np.int_), G._as_min_dtype(1),
+                     0.6, 0.8, 1.3, 1)
+    assert plan.ce.tolist() == [0, 409, 819, 1228, 1638, 2048, 2457, 2867, 3276, 3686, 4096]
+    assert np.array_equal(plan.tff, oracle.threshold_factors([32, 48, 64, 128], 1.3))
+    assert plan.scf.dtype == np.float32 and plan.scf[1] == np.float32(1.0 / 48)
+    assert plan.params.nwin_freq == 4 and plan.params.background_iterations == 5
+    assert plan.r2[0].tolist() == [28, 277]
+
+
+def test_unique_baselines_and_row_slots():
+    a1 = np.array([0, 0, 1, 0, 1, 2, 0], np.int32)
+    a2 = np.array([1, 2, 2, 1, 1, 2, 0], np.int32)
+    ub = P.unique_baselines(a1, a2).view(np.int32).reshape(-1, 2)
+    # int64 order: antenna2 is the high word
+    assert ub.tolist() == [[0, 0], [0, 1], [1, 1], [0, 2], [1, 2], [2, 2]]
+    ubl = np.concatenate([np.arange(6, dtype=np.int32)[:, None], ub], 1)
+    tinv = np.array([0, 0, 0, 0, 1, 1, 1])
+    slot, t = P._row_slots(ubl, a1, a2, tinv, last_wins=True)
+    # rows 0 and 3 collide on (baseline 0-1, t=0): the later row wins
+    assert slot.tolist() == [-1, 3, 4, 1, 2, 5, 0]
+    slot, _ = P._row_slots(ubl[:3], a1, a2, tinv, last_wins=False)
+    assert slot.tolist() == [1, -1, -1, 1, 2, -1, 0]
+
+
+def test_stokes_corr_map():
+    m = tb.stokes_corr_map([9, 10, 11, 12])
+    assert m == {'I': (0, 3, 0.5 + 0j, 1, 1), 'Q': (0, 3, 0.5 + 0j, 1, -1),
+                 'U': (1, 2, 0.5 + 0j, 1, 1), 'V': (1, 2, -0.5j, 1, -1)}
+    assert tb.stokes_corr_map([9, 12]) .keys() == {'I', 'Q'}
+    assert tb.stokes_corr_map([5, 6, 7, 8])['U'] == (1, 2, -0.5j, 1, -1)
+
+
+def test_default_strategy_matches_yaml():
+    """tests/common.py restates tricolour/conf/default.yaml; check it against the
+    file when the reference checkout is present"""
+    import os
+    path = "/root/reference/tricolour/conf/default.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not available")
+    assert tb.strategy.load_strategies(path) == common.default_strategies()
+
+
+def test_window_statistics_container():
+    a, b = tb.WindowStatistics(4), tb.WindowStatistics(4)
+    a._counts_per_ant["x"] += 2
+    a._size_per_ant["x"] += 10
+    b._counts_per_ant["x"] += 3
+    b._size_per_ant["x"] += 10
+    b._counts_per_ddid[0] += np.arange(4, dtype=np.uint64)
+    b._bins_per_ddid[0] = np.arange(4.0)
+    c = tb.combine_window_stats([a, b])
+    assert c._counts_per_ant["x"] == 5 and c._size_per_ant["x"] == 20
+    assert c._counts_per_ddid[0].tolist() == [0, 1, 2, 3]
+    assert a._counts_per_ant["x"] == 2

@@ -202,6 +202,27 @@ def test_median_abs(backend):
             assert (got[p, k] == want) or (np.isnan(got[p, k]) and np.isnan(want))
 
 
+def test_median_abs_long_ranges(backend):
+    """ranges longer than one slice take the multi-block radix select"""
+    rs = np.random.RandomState(55)
+    shape = (2, 512, 1100) if big(backend) else (1, 80, 500)
+    d = (rs.standard_normal(shape) * 10 ** rs.uniform(-2, 1, shape)).astype(np.float32)
+    d[0, 3, :7] = 0.25  # ties
+    fl = rs.uniform(size=shape) < 0.3
+    for odd in (0, 1):
+        fl[0, 0, 0] = bool(odd)
+        ce = [0, shape[2]] if not big(backend) else [0, 600, shape[2]]
+        got = np.atleast_2d(G._median_abs(d, fl, ce))
+        for p in range(shape[0]):
+            for k in range(len(ce) - 1):
+                want = oracle._median_abs(d[p][:, ce[k]:ce[k + 1]], fl[p][:, ce[k]:ce[k + 1]])
+                assert got[p, k] == want, (p, k, got[p, k], want)
+    vis, flags = common.make_windows(1, 1, 64, 600, seed=56)
+    got = tb.uvcontsub_flagger(vis, flags, major_cycles=2, or_original_from_cycle=1, taylor_degrees=20, sigma=15.0)
+    want = oracle.uvcontsub_flagger(vis.copy(), flags, major_cycles=2, or_original_from_cycle=1, taylor_degrees=20, sigma=15.0)
+    assert (got != want).mean() <= 1e-4
+
+
 # --------------------------------------------------------- filters/background --
 def test_linearly_interpolate_nans(backend):
     y = np.array([np.nan, np.nan, 4.0, np.nan, np.nan, 10.0, np.nan, -2.0, np.nan, np.nan], np.float32)

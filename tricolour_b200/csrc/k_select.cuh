@@ -279,6 +279,8 @@ struct ChunkSelectArgs {
 
 #define TC_SEL_BINS 2048
 
+__device__ __forceinline__ void hist_add_agg(uint32_t *hist, uint32_t bin, bool active);
+
 __device__ __forceinline__ float cs_value(const ChunkSelectArgs &a, int64_t i, float sub)
 {
     float x = a.resid[i];
@@ -304,12 +306,21 @@ k_chunk_select(ChunkSelectArgs a)
         const uint32_t dmask = pass == 2 ? 1023u : 2047u;
         for (int b = tid; b < TC_SEL_BINS; b += nt) hist[b] = 0;
         __syncthreads();
-        for (int64_t i = lo + tid; i < hi; i += nt) {
-            if (a.flags[i]) continue;
-            float x = cs_value(a, i, sub);
-            if (a.skip_nan && x != x) continue;
-            uint32_t k = f2key(x);
-            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
+        for (int64_t i0 = lo; i0 < hi; i0 += nt) {
+            int64_t i = i0 + tid;
+            bool act = i < hi;
+            uint32_t bin = 0;
+            if (act) {
+                act = a.flags[i] == 0;
+                if (act) {
+                    float x = cs_value(a, i, sub);
+                    if (a.skip_nan && x != x) act = false;
+                    uint32_t k = f2key(x);
+                    if ((k & himask) != prefix) act = false;
+                    bin = (k >> shift) & dmask;
+                }
+            }
+            hist_add_agg(hist, bin, act);
         }
         __syncthreads();
         if (tid == 0) {
@@ -381,9 +392,220 @@ k_chunk_select(ChunkSelectArgs a)
     }
 }
 
+// ----------------------------------------------------------------------------
+// Multi-block variant for long ranges (whole planes in uvcontsub, very wide
+// chunks): the same three digit passes, but every range is cut into slices that
+// separate blocks histogram concurrently (shared-memory histogram per block,
+// flushed with global atomics), with a tiny "pick" kernel between passes.
+// ----------------------------------------------------------------------------
+struct SelState {
+    uint32_t prefix, remaining, total, best;
+    double med;
+};
+
+#define TC_SEL_SLICE 32768
+
+// warp-aggregated histogram increment: lanes with the same bin elect a leader
+__device__ __forceinline__ void hist_add_agg(uint32_t *hist, uint32_t bin, bool active)
+{
+#ifdef TC_EMU
+    if (active) atomicAdd(&hist[bin], 1u);
+#else
+    unsigned peers = __match_any_sync(TC_FULL_MASK, active ? bin : 0xffffffffu);
+    if (active && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+#endif
+}
+
+__global__ void __launch_bounds__(1024)
+k_sel_hist(ChunkSelectArgs a, const SelState *__restrict__ st, uint32_t *__restrict__ ghist, int pass)
+{
+    __shared__ uint32_t hist[TC_SEL_BINS];
+    const int range = blockIdx.y;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
+    int64_t hi = lo + TC_SEL_SLICE;
+    if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    if (lo >= hi) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (pass > 0 && st[range].total == 0) return;
+    const float sub = a.sub ? (float)a.sub[range] : 0.0f;
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+    const uint32_t dmask = pass == 2 ? 1023u : 2047u;
+    const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? (2047u << 21) : ((2047u << 21) | (2047u << 10)));
+    const uint32_t prefix = pass == 0 ? 0u : st[range].prefix;
+    for (int b = tid; b < TC_SEL_BINS; b += nt) hist[b] = 0;
+    __syncthreads();
+    for (int64_t i0 = lo; i0 < hi; i0 += nt) {
+        int64_t i = i0 + tid;
+        bool act = i < hi;
+        uint32_t bin = 0;
+        if (act) {
+            act = a.flags[i] == 0;
+            if (act) {
+                float x = cs_value(a, i, sub);
+                if (a.skip_nan && x != x) act = false;
+                uint32_t k = f2key(x);
+                if ((k & himask) != prefix) act = false;
+                bin = (k >> shift) & dmask;
+            }
+        }
+        hist_add_agg(hist, bin, act);
+    }
+    __syncthreads();
+    uint32_t *gh = ghist + (size_t)range * TC_SEL_BINS;
+    for (int b = tid; b < TC_SEL_BINS; b += nt)
+        if (hist[b]) atomicAdd(&gh[b], hist[b]);
+}
+
+// one block per range: find the digit holding the wanted rank, clear the histogram
+__global__ void __launch_bounds__(256)
+k_sel_pick(SelState *__restrict__ st, uint32_t *__restrict__ ghist, int pass)
+{
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t s_digit, s_acc;
+    const int range = blockIdx.x, tid = threadIdx.x;
+    uint32_t *gh = ghist + (size_t)range * TC_SEL_BINS;
+    const int per = TC_SEL_BINS / 256;
+    uint32_t loc[TC_SEL_BINS / 256];
+    uint32_t sum = 0;
+    for (int k = 0; k < per; k++) { loc[k] = gh[tid * per + k]; sum += loc[k]; }
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int t = 0; t < 256; t++) total += part[t];
+        if (pass == 0) { st[range].total = total; st[range].remaining = total >> 1; st[range].prefix = 0; st[range].best = 0; }
+        uint32_t rem = st[range].remaining, acc = 0;
+        int seg = 0;
+        if (st[range].total > 0) {
+            for (seg = 0; seg < 255; seg++) {
+                if (rem < acc + part[seg]) break;
+                acc += part[seg];
+            }
+        }
+        s_digit = (uint32_t)seg;
+        s_acc = acc;
+    }
+    __syncthreads();
+    if (tid == (int)s_digit && st[range].total > 0) {
+        uint32_t rem = st[range].remaining, acc = s_acc;
+        uint32_t digit = tid * per;
+        for (int k = 0; k < per; k++) {
+            if (rem < acc + loc[k]) { digit = tid * per + k; break; }
+            acc += loc[k];
+        }
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        st[range].remaining = rem - acc;
+        st[range].prefix |= digit << shift;
+    }
+    for (int k = 0; k < per; k++) gh[tid * per + k] = 0;
+}
+
+// largest key below the selected one (needed for even counts, see the
+// single-block kernel)
+__global__ void __launch_bounds__(1024)
+k_sel_lower(ChunkSelectArgs a, SelState *__restrict__ st)
+{
+    const int range = blockIdx.y;
+    const SelState s = st[range];
+    if (s.total == 0 || (s.total & 1u) || s.remaining != 0) return;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
+    int64_t hi = lo + TC_SEL_SLICE;
+    if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    const float sub = a.sub ? (float)a.sub[range] : 0.0f;
+    uint32_t best = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (a.flags[i]) continue;
+        float x = cs_value(a, i, sub);
+        if (a.skip_nan && x != x) continue;
+        uint32_t k = f2key(x);
+        if (k < s.prefix && k > best) best = k;
+    }
+    best = warp_max_u(best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(&st[range].best, best);
+}
+
+__global__ void __launch_bounds__(128)
+k_sel_finish(ChunkSelectArgs a, SelState *__restrict__ st, int nranges)
+{
+    int range = blockIdx.x * blockDim.x + threadIdx.x;
+    if (range >= nranges) return;
+    SelState s = st[range];
+    double med = NAN;
+    if (s.total > 0) {
+        float upper = key2f(s.prefix), lower = upper;
+        if (!(s.total & 1u) && s.remaining == 0) lower = key2f(s.best);
+        med = median_from_pair(lower, upper, (int)s.total);
+    }
+    st[range].med = med;
+    if (a.medians) a.medians[range] = med;
+}
+
+__global__ void __launch_bounds__(1024)
+k_sel_update(ChunkSelectArgs a, const SelState *__restrict__ st)
+{
+    const int range = blockIdx.y;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
+    int64_t hi = lo + TC_SEL_SLICE;
+    if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    const double med = st[range].med;
+    if (a.mode == CS_BACKGROUND) {
+        double thr = med * a.thr_mult;
+        if (thr != thr) return;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            if ((double)a.resid[i] > thr) a.flags[i] = 1;
+    } else if (a.mode == CS_UVCONTSUB) {
+        if (a.uv_unflagged[range] == 0) return;
+        float thr = a.uv_sigma * (float)med;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            bool nf = a.resid[i] > thr;
+            if (a.uv_replace) a.flags[i] = nf ? 1 : 0;
+            else if (nf) a.flags[i] = 1;
+        }
+    }
+}
+
+static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a, int64_t nranges, int64_t max_range)
+{
+    tc_mark mark = tc_arena_mark(c);
+    SelState *st;
+    uint32_t *gh;
+    TC_TRY(tc_alloc(c, (size_t)nranges, &st));
+    TC_TRY(tc_alloc(c, (size_t)nranges * TC_SEL_BINS, &gh));
+    TC_CUDA(cudaMemsetAsync(gh, 0, sizeof(uint32_t) * (size_t)nranges * TC_SEL_BINS, c->stream));
+    unsigned slices = (unsigned)((max_range + TC_SEL_SLICE - 1) / TC_SEL_SLICE);
+    tc_prof_begin(c, TCP_CHUNK_SELECT);
+    for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
+        unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);
+        ChunkSelectArgs b = a;
+        b.range_lo += r0; b.range_hi += r0;
+        if (b.sub) b.sub += r0;
+        if (b.medians) b.medians += r0;
+        if (b.uv_unflagged) b.uv_unflagged += r0;
+        dim3 grid(slices, nr);
+        for (int pass = 0; pass < 3; pass++) {
+            TC_LAUNCH(k_sel_hist, grid, 1024, 0, c->stream, b, st + r0, gh + r0 * TC_SEL_BINS, pass);
+            TC_LAUNCH(k_sel_pick, nr, 256, 0, c->stream, st + r0, gh + r0 * TC_SEL_BINS, pass);
+        }
+        TC_LAUNCH(k_sel_lower, grid, 1024, 0, c->stream, b, st + r0);
+        TC_LAUNCH_NOSYNC(k_sel_finish, tc_blocks_for(nr, 128), 128, 0, c->stream, b, st + r0, (int)nr);
+        c->launches += 8;
+        if (a.mode != CS_REPORT) {
+            TC_LAUNCH_NOSYNC(k_sel_update, grid, 1024, 0, c->stream, b, st + r0);
+            c->launches++;
+        }
+    }
+    tc_prof_end(c);
+    TC_KERNEL_CHECK();
+    tc_arena_release(c, mark);
+    return TC_OK;
+}
+
 static int launch_chunk_select(tc_context *c, const ChunkSelectArgs &a, int64_t nranges, int64_t max_range)
 {
     if (nranges == 0) return TC_OK;
+    // long ranges (or too few of them to fill the GPU) go through the sliced path
+    if (max_range > 8 * TC_SEL_SLICE || (max_range > TC_SEL_SLICE && nranges < 2 * (int64_t)c->sm_count))
+        return launch_chunk_select_multi(c, a, nranges, max_range);
     int bd = 1024;
     if (max_range <= 4096) bd = 128;
     else if (max_range <= 32768) bd = 256;

@@ -87,8 +87,9 @@ def make_block_torch(nbl, ncorr, T, F, bl0, ubl, device, seed):
     im = amp * torch.sin(ph) + noise[..., 1] * bp
     del noise
     rs = np.random.RandomState(seed)
-    for f in rs.choice(F, max(F // 100, 1), replace=False):
-        re[:, :, :, f] += float(rs.uniform(10, 100)) * 0.1 * float(bp[f])
+    for f in rs.choice(max(F - 4, 1), max(F // 1000, 1), replace=False):
+        wband = rs.randint(1, 4)   # persistent RFI: a few narrow bands
+        re[:, :, :, f:f + wband] += float(rs.uniform(5, 40)) * 0.1 * bp[f:f + wband]
     for tt in rs.choice(T, max(T // 200, 1), replace=False):
         re[:, :, tt, :] += float(rs.uniform(5, 20)) * 0.1 * bp
     for _ in range(20 * nbl):

@@ -108,9 +108,11 @@ def make_windows(nbl, ncorr, T, F, seed=20261019, ubl=None):
     phase = np.exp(1j * rs.uniform(0, 2 * np.pi, (nbl, ncorr, 1, 1)))
     vis = (amp * phase + sigma * noise / np.sqrt(2)).astype(np.complex64)
     # persistent channels, broadband dumps, blobs, a faint persistent channel
-    nper = max(F // 100, 1)
-    for f in rs.choice(F, nper, replace=False):
-        vis[:, :, :, f] += (rs.uniform(10, 100) * sigma[..., f]).astype(np.complex64)
+    # persistent RFI: a few narrow bands (real RFI is clustered, not spread evenly)
+    nband = max(F // 1000, 1)
+    for f in rs.choice(max(F - 4, 1), nband, replace=False):
+        wband = rs.randint(1, 4)
+        vis[:, :, :, f:f + wband] += (rs.uniform(5, 40) * sigma[..., f:f + wband]).astype(np.complex64)
     for t in rs.choice(T, max(T // 200, 1), replace=False):
         vis[:, :, t, :] += (rs.uniform(5, 20) * sigma[0, 0, 0, :]).astype(np.complex64)
     for _ in range(20):

@@ -50,133 +50,113 @@ struct FilterArgs {
     int64_t gring_stride;
 };
 
-#define TC_FILT_U 4  // ticks per unrolled group / prefetch distance
+#define TC_FILT_U 8   // ticks per group: prefetch distance and output staging depth
+#define TC_FILT_LPW 4 // lines per warp
 
+// Warp-cooperative form.  The 32 lanes of a warp are 4 lines x 2 arrays x 4
+// passes: lane = pass*8 + array*4 + line.  Every lane runs the SAME loop body
+//     s += entering;  emit = (float)s;  s -= leaving
+// on its own accumulator and its own 2r-deep delay line in shared memory
+// ([slot][lane], conflict free); pass p+1 picks up what pass p emitted one tick
+// earlier with a warp shuffle (lane - 8).  Splitting a line over eight lanes
+// keeps the shared-memory footprint per line unchanged (the delay lines) but
+// gives the SM eight times as many warps to hide the FP64 / convert latencies.
+// Pass-0 lanes fetch the input one group (8 ticks) ahead; pass-3 lanes park
+// their outputs in a small staging tile that all 32 lanes drain every 8 ticks
+// (division by d^4, background = value / weight, coalesced 16-byte stores).
 template <bool SMEM_RING, int MODE_IN, int MODE_OUT>
 __global__ void k_box_filter(FilterArgs a)
 {
-    TC_DYN_SMEM(float, sring);
-    const int L = 2 * a.r;
-    float *ring;
-    int64_t rstride, rtid;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
-    if (SMEM_RING) { ring = sring; rstride = blockDim.x; rtid = threadIdx.x; }
-    else { ring = a.gring; rstride = a.gring_stride; rtid = gtid; }
-    const int n = a.n, r2 = 2 * a.r, r4 = 4 * a.r;
+    TC_DYN_SMEM(float, smem);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;            // warp in block
+    const int nwb = blockDim.x >> 5;
+    const int pass = lane >> 3, arr = (lane >> 2) & 1, q = lane & 3;
+    const int L = 2 * a.r, r2 = 2 * a.r, r4 = 4 * a.r;
+    const int n = a.n;
     const int64_t nj = a.nj;
-    const int64_t lstride = (int64_t)L * rstride;
-    const int nticks = n + r4 + 3;  // pass p lags pass 1 by p-1 ticks
+    const int64_t ngroups = (a.nlines + TC_FILT_LPW - 1) / TC_FILT_LPW;
+    const int64_t gwarp = (int64_t)blockIdx.x * nwb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * nwb;
+    // per-warp shared memory: staging tile [8 ticks][8 outputs] then the ring [L][32]
+    float *stg = smem + (size_t)wib * (64 + (SMEM_RING ? (size_t)L * 32 : 0));
+    float *ring = SMEM_RING ? (stg + 64) : (a.gring + (size_t)gwarp * L * 32);
+    const int nticks = n + r4 + 3;
+    // window of local ticks in which this pass really receives a sample
+    const int add_lo = pass == 3 ? r2 : 0;
+    const int add_hi = pass == 0 ? n : (pass == 1 ? n + r2 : 0x7fffffff);
 
-    for (int64_t line = gtid; line < a.nlines; line += gthreads) {
-        const int64_t plane = line / nj;
-        const int64_t base = plane * (int64_t)n * nj + (line - plane * nj);
-        double s1v = 0, s1w = 0, s2v = 0, s2w = 0, s3v = 0, s3w = 0, s4v = 0, s4w = 0;
-        float y1v = 0.f, y1w = 0.f, y2v = 0.f, y2w = 0.f, y3v = 0.f, y3w = 0.f;
+    for (int64_t grp = gwarp; grp < ngroups; grp += nwarps) {
+        const int64_t line = grp * TC_FILT_LPW + q;
+        const bool line_ok = line < a.nlines;
+        const int64_t plane = line_ok ? line / nj : 0;
+        const int64_t base = line_ok ? plane * (int64_t)n * nj + (line - plane * nj) : 0;
+        const bool loader = pass == 0 && line_ok;
+        double s = 0.0;
+        float y = 0.f;
         int slot = 0;
+        float cur[TC_FILT_U], nxt[TC_FILT_U];
 
-        // raw prefetch registers: entering sample (tick m) and leaving sample (m - 2r)
-        float ea[TC_FILT_U], eb[TC_FILT_U], la[TC_FILT_U], lb[TC_FILT_U];
-        float nea[TC_FILT_U], neb[TC_FILT_U], nla[TC_FILT_U], nlb[TC_FILT_U];
-
-#define TC_FILT_LOAD(m, A, B)                                                        \
-        do {                                                                         \
-            A = 0.f; B = 0.f;                                                        \
-            if ((m) >= 0 && (m) < n) {                                               \
-                int64_t idx_ = base + (int64_t)(m) * nj;                             \
-                if (MODE_IN == FIN_MASKED) { A = a.data[idx_]; B = a.flags[idx_] ? 0.f : 1.f; } \
-                else { A = a.data[idx_]; B = a.win[idx_]; }                          \
-            }                                                                        \
+#define TC_FILT_LOAD(m, OUT)                                                          \
+        do {                                                                          \
+            OUT = 0.f;                                                                \
+            if (loader && (m) < n) {                                                  \
+                const int64_t idx_ = base + (int64_t)(m) * nj;                        \
+                if (MODE_IN == FIN_MASKED) {                                          \
+                    const bool fl_ = a.flags[idx_] != 0;                              \
+                    if (arr == 0) { const float d_ = a.data[idx_]; OUT = fl_ ? 0.f : d_; } \
+                    else OUT = fl_ ? 0.f : 1.f;                                       \
+                } else {                                                              \
+                    OUT = arr == 0 ? a.data[idx_] : a.win[idx_];                      \
+                }                                                                     \
+            }                                                                         \
         } while (0)
 
 #pragma unroll
-        for (int k = 0; k < TC_FILT_U; k++) {
-            TC_FILT_LOAD(k, ea[k], eb[k]);
-            TC_FILT_LOAD(k - r2, la[k], lb[k]);
-        }
+        for (int k = 0; k < TC_FILT_U; k++) TC_FILT_LOAD(k, cur[k]);
 
         for (int t0 = 0; t0 < nticks; t0 += TC_FILT_U) {
-            // issue the loads of the next group first
+#pragma unroll
+            for (int k = 0; k < TC_FILT_U; k++) TC_FILT_LOAD(t0 + TC_FILT_U + k, nxt[k]);
 #pragma unroll
             for (int k = 0; k < TC_FILT_U; k++) {
-                const int m = t0 + TC_FILT_U + k;
-                TC_FILT_LOAD(m, nea[k], neb[k]);
-                TC_FILT_LOAD(m - r2, nla[k], nlb[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < TC_FILT_U; k++) {
-                const int tick = t0 + k;
-                float *rp = ring + ((int64_t)slot * rstride + rtid);
-                // ---- pass 4 (local tick tick-3): entering x3 = y3 of the previous tick
-                {
-                    const int m = tick - 3;
-                    const bool warm = m >= r2;
-                    if (warm) { s4v += (double)y3v; s4w += (double)y3w; }
-                    const float y4v = (float)s4v, y4w = (float)s4w;
-                    if (m >= 0) {
-                        const float ov = warm ? rp[4 * lstride] : 0.f, ow = warm ? rp[5 * lstride] : 0.f;
-                        rp[4 * lstride] = warm ? y3v : 0.f;
-                        rp[5 * lstride] = warm ? y3w : 0.f;
-                        s4v -= (double)ov; s4w -= (double)ow;
-                    }
-                    if (m >= r4 && m < n + r4) {
-                        const int64_t idx = base + (int64_t)(m - r4) * nj;
-                        const float fv = y4v / a.div, fw = y4w / a.div;
-                        if (MODE_OUT == FOUT_PAIR) {
-                            a.vout[idx] = fv;
-                            a.wout[idx] = fw;
-                        } else {
-                            float bg = (fw == 0.f) ? NAN : fv / fw;
-                            if (MODE_OUT == FOUT_RESID) bg = fabsf(a.data2[idx] - bg);
-                            a.vout[idx] = bg;
-                        }
-                    }
-                }
-                // ---- pass 3 (local tick tick-2): entering x2 = y2 of the previous tick
-                {
-                    const int m = tick - 2;
-                    if (m >= 0) {
-                        s3v += (double)y2v; s3w += (double)y2w;
-                        y3v = (float)s3v; y3w = (float)s3w;
-                        const bool warm = m >= r2;
-                        const float ov = warm ? rp[2 * lstride] : 0.f, ow = warm ? rp[3 * lstride] : 0.f;
-                        rp[2 * lstride] = y2v; rp[3 * lstride] = y2w;
-                        s3v -= (double)ov; s3w -= (double)ow;
-                    }
-                }
-                // ---- pass 2 (local tick tick-1): entering x1 = y1 of the previous tick
-                {
-                    const int m = tick - 1;
-                    if (m >= 0) {
-                        const bool valid = m < n + r2;  // x1 runs off the padded array afterwards
-                        if (valid) { s2v += (double)y1v; s2w += (double)y1w; }
-                        y2v = (float)s2v; y2w = (float)s2w;
-                        const bool warm = m >= r2;
-                        const float ov = warm ? rp[0] : 0.f, ow = warm ? rp[lstride] : 0.f;
-                        rp[0] = valid ? y1v : 0.f; rp[lstride] = valid ? y1w : 0.f;
-                        s2v -= (double)ov; s2w -= (double)ow;
-                    }
-                }
-                // ---- pass 1 (local tick tick): entering line[m], leaving line[m-2r]
-                {
-                    const int m = tick;
-                    if (m < n + r2) {
-                        float ev = ea[k], ew = eb[k];
-                        if (MODE_IN == FIN_MASKED) ev = (ew != 0.f) ? ev : 0.f;
-                        if (m < n) { s1v += (double)ev; s1w += (double)ew; }
-                        y1v = (float)s1v; y1w = (float)s1w;
-                        if (m >= r2) {
-                            float lv = la[k], lw = lb[k];
-                            if (MODE_IN == FIN_MASKED) lv = (lw != 0.f) ? lv : 0.f;
-                            s1v -= (double)lv; s1w -= (double)lw;
-                        }
-                    }
-                }
+                const int m = t0 + k - pass;  // local tick of this lane's pass
+                const float prev = __shfl_up_sync(TC_FULL_MASK, y, 8);
+                const float uin = pass == 0 ? cur[k] : prev;
+                const float u = (m >= add_lo && m < add_hi) ? uin : 0.f;
+                float *rp = ring + ((size_t)slot * 32 + lane);
+                const float old = (m >= r2) ? *rp : 0.f;
+                *rp = u;
+                s += (double)u;
+                y = (float)s;
+                s -= (double)old;
+                if (pass == 3) stg[k * 8 + (lane - 24)] = y;
                 slot++;
                 if (slot == L) slot = 0;
             }
+            __syncwarp();
+            // drain: lane -> (tick kk of the group, line qq); pass-3 local tick = t0+kk-3
+            {
+                const int kk = lane >> 2, qq = lane & 3;
+                const int jout = t0 + kk - 3 - r4;
+                const int64_t oline = grp * TC_FILT_LPW + qq;
+                if (jout >= 0 && jout < n && oline < a.nlines) {
+                    const int64_t op = oline / nj;
+                    const int64_t idx = op * (int64_t)n * nj + (oline - op * nj) + (int64_t)jout * nj;
+                    const float fv = stg[kk * 8 + qq] / a.div, fw = stg[kk * 8 + 4 + qq] / a.div;
+                    if (MODE_OUT == FOUT_PAIR) {
+                        a.vout[idx] = fv;
+                        a.wout[idx] = fw;
+                    } else {
+                        float bg = (fw == 0.f) ? NAN : fv / fw;
+                        if (MODE_OUT == FOUT_RESID) bg = fabsf(a.data2[idx] - bg);
+                        a.vout[idx] = bg;
+                    }
+                }
+            }
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < TC_FILT_U; k++) { ea[k] = nea[k]; eb[k] = neb[k]; la[k] = nla[k]; lb[k] = nlb[k]; }
+            for (int k = 0; k < TC_FILT_U; k++) cur[k] = nxt[k];
         }
 #undef TC_FILT_LOAD
     }
@@ -213,7 +193,7 @@ static int launch_box_filter_mode(tc_context *c, const FilterArgs &a, unsigned g
         if (smem > 48 * 1024)                                                                         \
             TC_CUDA(cudaFuncSetAttribute(k_box_filter<SMEM_RING, MI, MO>,                              \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        TC_LAUNCH_NOSYNC((k_box_filter<SMEM_RING, MI, MO>), grid, bd, smem, c->stream, a);            \
+        TC_LAUNCH((k_box_filter<SMEM_RING, MI, MO>), grid, bd, smem, c->stream, a);            \
         return TC_OK;                                                                                 \
     }
     TC_FILT_CASE(FIN_MASKED, FOUT_PAIR)
@@ -231,28 +211,27 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
     if (a.nlines == 0 || a.n == 0) return TC_OK;
     a.div = tc_f32_pow4(2 * (int64_t)a.r + 1);
     tc_prof_begin(c, TCP_BOX_FILTER);
-    const size_t per_thread = (size_t)6 * 2 * a.r * sizeof(float);
+    const int64_t ngroups = (a.nlines + TC_FILT_LPW - 1) / TC_FILT_LPW;
+    const size_t per_warp = ((size_t)2 * a.r * 32 + 64) * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;
-    int bd = (int)(smem_cap / per_thread);
-    bd = bd / 32 * 32;
-    if (bd > 128) bd = 128;
-    if (bd >= 32) {
-        // keep several blocks per SM when the delay lines are short
-        while (bd > 32 && (int64_t)tc_blocks_for(a.nlines, bd) < 2 * (int64_t)c->sm_count) bd -= 32;
-        size_t smem = per_thread * bd;
-        TC_TRY(launch_box_filter_mode<true>(c, a, tc_blocks_for(a.nlines, bd), bd, smem));
+    if (per_warp <= smem_cap) {
+        // 4 warps (16 lines) per block unless the delay lines are too deep
+        int wpb = (int)(smem_cap / per_warp);
+        if (wpb > 4) wpb = 4;
+        while (wpb > 1 && (ngroups + wpb - 1) / wpb < 2 * (int64_t)c->sm_count) wpb--;
+        size_t smem = per_warp * wpb;
+        unsigned grid = (unsigned)((ngroups + wpb - 1) / wpb);
+        TC_TRY(launch_box_filter_mode<true>(c, a, grid, wpb * 32, smem));
     } else {
-        // delay lines too deep for shared memory: persistent threads with an
-        // L2-resident global ring
-        int bd2 = 64;
-        int64_t blocks = (int64_t)c->sm_count * 2;
-        if (blocks > (int64_t)tc_blocks_for(a.nlines, bd2)) blocks = tc_blocks_for(a.nlines, bd2);
-        int64_t threads = blocks * bd2;
+        // delay lines too deep for shared memory: persistent warps, L2-resident ring
+        int wpb = 2;
+        int64_t blocks = (int64_t)c->sm_count * 4;
+        if (blocks > (ngroups + wpb - 1) / wpb) blocks = (ngroups + wpb - 1) / wpb;
         float *g = nullptr;
-        TC_TRY(tc_alloc(c, (size_t)threads * 6 * 2 * a.r, &g));
+        TC_TRY(tc_alloc(c, (size_t)blocks * wpb * 2 * a.r * 32, &g));
         a.gring = g;
-        a.gring_stride = threads;
-        TC_TRY(launch_box_filter_mode<false>(c, a, (unsigned)blocks, bd2, 0));
+        a.gring_stride = 0;
+        TC_TRY(launch_box_filter_mode<false>(c, a, (unsigned)blocks, wpb * 32, 64 * sizeof(float) * wpb));
     }
     tc_prof_end(c);
     c->launches++;

@@ -85,6 +85,7 @@ __global__ void k_box_filter(FilterArgs a)
     // window of local ticks in which this pass really receives a sample
     const int add_lo = pass == 3 ? r2 : 0;
     const int add_hi = pass == 0 ? n : (pass == 1 ? n + r2 : 0x7fffffff);
+    const int kk = lane >> 2, qq = lane & 3;     // drain role: (tick in group, line)
 
     for (int64_t grp = gwarp; grp < ngroups; grp += nwarps) {
         const int64_t line = grp * TC_FILT_LPW + q;
@@ -92,73 +93,84 @@ __global__ void k_box_filter(FilterArgs a)
         const int64_t plane = line_ok ? line / nj : 0;
         const int64_t base = line_ok ? plane * (int64_t)n * nj + (line - plane * nj) : 0;
         const bool loader = pass == 0 && line_ok;
+        const int64_t oline = grp * TC_FILT_LPW + qq;
+        const bool oline_ok = oline < a.nlines;
+        const int64_t oplane = oline_ok ? oline / nj : 0;
+        const int64_t obase = oline_ok ? oplane * (int64_t)n * nj + (oline - oplane * nj) : 0;
+        const float *pin = (MODE_IN == FIN_PAIR && arr == 1) ? a.win + base : a.data + base;
+        const u8 *pfl = MODE_IN == FIN_MASKED ? a.flags + base : nullptr;
         double s = 0.0;
         float y = 0.f;
-        int slot = 0;
-        float cur[TC_FILT_U], nxt[TC_FILT_U];
+        float *rp = ring + lane;
+        float *const rend = ring + (size_t)L * 32 + lane;
+        // three rotating input buffers: loads run two groups (16 ticks) ahead
+        float x0[TC_FILT_U], x1[TC_FILT_U], x2[TC_FILT_U];
 
-#define TC_FILT_LOAD(m, OUT)                                                          \
-        do {                                                                          \
-            OUT = 0.f;                                                                \
-            if (loader && (m) < n) {                                                  \
-                const int64_t idx_ = base + (int64_t)(m) * nj;                        \
-                if (MODE_IN == FIN_MASKED) {                                          \
-                    const bool fl_ = a.flags[idx_] != 0;                              \
-                    if (arr == 0) { const float d_ = a.data[idx_]; OUT = fl_ ? 0.f : d_; } \
-                    else OUT = fl_ ? 0.f : 1.f;                                       \
-                } else {                                                              \
-                    OUT = arr == 0 ? a.data[idx_] : a.win[idx_];                      \
-                }                                                                     \
-            }                                                                         \
-        } while (0)
-
-#pragma unroll
-        for (int k = 0; k < TC_FILT_U; k++) TC_FILT_LOAD(k, cur[k]);
-
-        for (int t0 = 0; t0 < nticks; t0 += TC_FILT_U) {
-#pragma unroll
-            for (int k = 0; k < TC_FILT_U; k++) TC_FILT_LOAD(t0 + TC_FILT_U + k, nxt[k]);
-#pragma unroll
-            for (int k = 0; k < TC_FILT_U; k++) {
-                const int m = t0 + k - pass;  // local tick of this lane's pass
-                const float prev = __shfl_up_sync(TC_FULL_MASK, y, 8);
-                const float uin = pass == 0 ? cur[k] : prev;
-                const float u = (m >= add_lo && m < add_hi) ? uin : 0.f;
-                float *rp = ring + ((size_t)slot * 32 + lane);
-                const float old = (m >= r2) ? *rp : 0.f;
-                *rp = u;
-                s += (double)u;
-                y = (float)s;
-                s -= (double)old;
-                if (pass == 3) stg[k * 8 + (lane - 24)] = y;
-                slot++;
-                if (slot == L) slot = 0;
-            }
-            __syncwarp();
-            // drain: lane -> (tick kk of the group, line qq); pass-3 local tick = t0+kk-3
-            {
-                const int kk = lane >> 2, qq = lane & 3;
-                const int jout = t0 + kk - 3 - r4;
-                const int64_t oline = grp * TC_FILT_LPW + qq;
-                if (jout >= 0 && jout < n && oline < a.nlines) {
-                    const int64_t op = oline / nj;
-                    const int64_t idx = op * (int64_t)n * nj + (oline - op * nj) + (int64_t)jout * nj;
-                    const float fv = stg[kk * 8 + qq] / a.div, fw = stg[kk * 8 + 4 + qq] / a.div;
-                    if (MODE_OUT == FOUT_PAIR) {
-                        a.vout[idx] = fv;
-                        a.wout[idx] = fw;
-                    } else {
-                        float bg = (fw == 0.f) ? NAN : fv / fw;
-                        if (MODE_OUT == FOUT_RESID) bg = fabsf(a.data2[idx] - bg);
-                        a.vout[idx] = bg;
-                    }
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < TC_FILT_U; k++) cur[k] = nxt[k];
+#define TC_FILT_LOADG(X, T0)                                                           \
+        _Pragma("unroll")                                                              \
+        for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                       \
+            const int m_ = (T0) + k_;                                                  \
+            X[k_] = 0.f;                                                               \
+            if (loader && m_ < n) {                                                    \
+                const int64_t off_ = (int64_t)m_ * nj;                                 \
+                if (MODE_IN == FIN_MASKED) {                                           \
+                    const bool fl_ = pfl[off_] != 0;                                   \
+                    if (arr == 0) { const float d_ = pin[off_]; X[k_] = fl_ ? 0.f : d_; } \
+                    else X[k_] = fl_ ? 0.f : 1.f;                                      \
+                } else {                                                               \
+                    X[k_] = pin[off_];                                                 \
+                }                                                                      \
+            }                                                                          \
         }
-#undef TC_FILT_LOAD
+
+#define TC_FILT_GROUP(X, T0)                                                           \
+        {                                                                              \
+            _Pragma("unroll")                                                          \
+            for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                   \
+                const int m_ = (T0) + k_ - pass;                                       \
+                const float prev_ = __shfl_up_sync(TC_FULL_MASK, y, 8);                \
+                const float uin_ = pass == 0 ? X[k_] : prev_;                          \
+                const float u_ = (m_ >= add_lo && m_ < add_hi) ? uin_ : 0.f;           \
+                const float old_ = (m_ >= r2) ? *rp : 0.f;                             \
+                *rp = u_;                                                              \
+                s += (double)u_;                                                       \
+                y = (float)s;                                                          \
+                s -= (double)old_;                                                     \
+                if (pass == 3) stg[k_ * 8 + (lane - 24)] = y;                          \
+                rp += 32;                                                              \
+                if (rp == rend) rp = ring + lane;                                      \
+            }                                                                          \
+            __syncwarp();                                                              \
+            const int jout_ = (T0) + kk - 3 - r4;                                      \
+            if (jout_ >= 0 && jout_ < n && oline_ok) {                                 \
+                const int64_t idx_ = obase + (int64_t)jout_ * nj;                      \
+                const float fv_ = stg[kk * 8 + qq] / a.div, fw_ = stg[kk * 8 + 4 + qq] / a.div; \
+                if (MODE_OUT == FOUT_PAIR) {                                           \
+                    a.vout[idx_] = fv_;                                                \
+                    a.wout[idx_] = fw_;                                                \
+                } else {                                                               \
+                    float bg_ = (fw_ == 0.f) ? NAN : fv_ / fw_;                        \
+                    if (MODE_OUT == FOUT_RESID) bg_ = fabsf(a.data2[idx_] - bg_);      \
+                    a.vout[idx_] = bg_;                                                \
+                }                                                                      \
+            }                                                                          \
+            __syncwarp();                                                              \
+        }
+
+        TC_FILT_LOADG(x0, 0)
+        TC_FILT_LOADG(x1, TC_FILT_U)
+        for (int t0 = 0; t0 < nticks; t0 += 3 * TC_FILT_U) {
+            TC_FILT_LOADG(x2, t0 + 2 * TC_FILT_U)
+            TC_FILT_GROUP(x0, t0)
+            if (t0 + TC_FILT_U >= nticks) break;
+            TC_FILT_LOADG(x0, t0 + 3 * TC_FILT_U)
+            TC_FILT_GROUP(x1, t0 + TC_FILT_U)
+            if (t0 + 2 * TC_FILT_U >= nticks) break;
+            TC_FILT_LOADG(x1, t0 + 4 * TC_FILT_U)
+            TC_FILT_GROUP(x2, t0 + 2 * TC_FILT_U)
+        }
+#undef TC_FILT_LOADG
+#undef TC_FILT_GROUP
     }
 }
 

@@ -119,6 +119,64 @@ k_interp_nans(float *__restrict__ d, int64_t nlines, int64_t ninner, int64_t out
 #undef X
 }
 
+// Warp-per-line form for contiguous lines: two tile sweeps with ballots find,
+// for every NaN, the nearest valid sample on either side (`rv` is scratch for the
+// right neighbours), after which every sample is independent.  Writes
+// out = interp(bg), or out = minuend - interp(bg) when `minuend` is given
+// (flagging.py:962 fused).
+__global__ void __launch_bounds__(128)
+k_interp_nans_rows(const float *__restrict__ bg, const float *__restrict__ minuend,
+                   float *__restrict__ out, int *__restrict__ rv, int64_t nlines, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t line = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (line >= nlines) return;
+    const float *x = bg + line * (int64_t)n;
+    int *r = rv + line * (int64_t)n;
+    const int ntiles = (n + 31) / 32;
+    // backward sweep: index of the next valid sample at or after i (n if none)
+    int carry = n;
+    int nnan = 0;
+    for (int t = ntiles - 1; t >= 0; t--) {
+        const int i = t * 32 + lane;
+        const bool valid = i < n && !(x[i] != x[i]);
+        const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
+        const unsigned mm = m >> lane;
+        if (i < n) r[i] = mm ? i + __ffs((int)mm) - 1 : carry;
+        if (m) carry = t * 32 + __ffs((int)m) - 1;
+        nnan += (i < n && !valid) ? 1 : 0;
+    }
+    __syncwarp();
+    // forward sweep: previous valid sample at or before i (-1 if none), then fill
+    int carl = -1;
+    for (int t = 0; t < ntiles; t++) {
+        const int i = t * 32 + lane;
+        const float xi = i < n ? x[i] : 0.f;
+        const bool valid = i < n && !(xi != xi);
+        const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
+        const unsigned below = m & (0xffffffffu >> (31 - lane));
+        const int lv = below ? t * 32 + 31 - __clz((int)below) : carl;
+        if (m) carl = t * 32 + 31 - __clz((int)m);
+        if (i < n) {
+            float val = xi;
+            if (!valid) {
+                const int rr = r[i];
+                if (lv < 0 && rr >= n) val = 0.0f;
+                else if (lv < 0) val = x[rr];
+                else if (rr >= n) val = x[lv];
+                else {
+                    const float start = x[lv];
+                    // float32 difference, true division by an int64 -> float64
+                    const double grad = __ddiv_rn((double)(x[rr] - start), (double)(rr - lv));
+                    val = (float)__dadd_rn((double)start, __dmul_rn((double)(i - lv), grad));
+                }
+            }
+            out[line * (int64_t)n + i] = minuend ? minuend[line * (int64_t)n + i] - val : val;
+        }
+    }
+    (void)nnan;
+}
+
 // ----------------------------------------------------------------------------
 // S9 _sum_threshold1d (flagging.py:610-681) with _convolve_flags (582-607).
 // One thread scans one (line, chunk): for every window, a sequential float64

@@ -116,12 +116,15 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
 }
 
 // _get_background2d (flagging.py:516-579).  flags_* are the caller's flags
-// (not modified); the interpolated background lands in out_FT.
+// (not modified).  work_FT receives the filter outputs; the interpolated
+// background lands in out_TF, or minuend_TF - background when minuend_TF is
+// given (the `data -= background` of flagging.py:950/962 fused in).
 static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const float *data_TF,
                             const float *data_FT, const u8 *flags_TF, const u8 *flags_FT,
                             int iterations, const int64_t *radii, double reject,
                             const int64_t *range_lo, const int64_t *range_hi, int nchunks,
-                            int64_t max_range, float *out_FT)
+                            int64_t max_range, float *work_FT, float *out_TF,
+                            const float *minuend_TF)
 {
     int64_t N = np * (int64_t)T * Fa;
     bool need_tf = false;
@@ -135,21 +138,31 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
     for (int it = 0; it <= iterations; it++) {
         int64_t r0 = T == 1 ? 0 : radii[2 * it], r1 = radii[2 * it + 1];
         bool final_pass = it == iterations;
-        TC_TRY(dev_masked_filter(c, np, T, Fa, data_TF, data_FT, w, r0, r1, final_pass ? 0 : 1, out_FT));
+        TC_TRY(dev_masked_filter(c, np, T, Fa, data_TF, data_FT, w, r0, r1, final_pass ? 0 : 1, work_FT));
         if (final_pass) break;
         ChunkSelectArgs s;
         memset(&s, 0, sizeof(s));
-        s.resid = out_FT; s.flags = w.fl_FT; s.range_lo = range_lo; s.range_hi = range_hi;
+        s.resid = work_FT; s.flags = w.fl_FT; s.range_lo = range_lo; s.range_hi = range_hi;
         s.thr_mult = MAD_NORMAL * reject; s.mode = CS_BACKGROUND; s.take_abs = 0; s.medians = nullptr;
         TC_TRY(launch_chunk_select(c, s, np * nchunks, max_range));
         // the next time-axis filter reads the flags in TF
         bool next_tf = need_tf && radii[2 * (it + 1)] > 0;
         if (next_tf) TC_TRY(launch_transpose<u8>(c, w.fl_FT, w.fl_TF, np, Fa, T));
     }
-    // _linearly_interpolate_nans along frequency for every (plane, dump)
+    // _linearly_interpolate_nans along frequency for every (plane, dump): one
+    // warp per contiguous (T,F) row
+    const float *bg_TF = work_FT;
+    if (T != 1) {
+        float *tmp;
+        TC_TRY(tc_alloc(c, (size_t)N, &tmp));
+        TC_TRY(launch_transpose<float>(c, work_FT, tmp, np, Fa, T));
+        bg_TF = tmp;
+    }
+    int *rv;
+    TC_TRY(tc_alloc(c, (size_t)N, &rv));
     tc_prof_begin(c, TCP_INTERP);
-    TC_LAUNCH_NOSYNC(k_interp_nans, tc_blocks_for(np * T, 128), 128, 0, c->stream, out_FT, np * (int64_t)T,
-                     (int64_t)T, (int64_t)T * Fa, (int64_t)1, Fa, (int64_t)T);
+    TC_LAUNCH(k_interp_nans_rows, tc_blocks_for(np * (int64_t)T * 32, 128), 128, 0, c->stream, bg_TF, minuend_TF,
+              out_TF, rv, np * (int64_t)T, Fa);
     tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
@@ -271,12 +284,11 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     // spectrum background (flagging.py:945-949) and its SumThreshold (950-952)
     int64_t *slo, *shi, smax;
     TC_TRY(dev_make_ranges(c, np, 1, Fa, p->freq_chunk_ends, nce, &slo, &shi, &smax));
+    float *spec_res;
+    TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_res));
     TC_TRY(dev_background2d(c, np, 1, Fa, spec_data, spec_data, spec_fl, spec_fl, iters, p->radii_spec,
-                            p->background_reject, slo, shi, nchunks, smax, spec_bg));
-    TC_LAUNCH_NOSYNC(k_sub, tc_blocks_for(np * Fa, 256), 256, 0, c->stream, spec_data, spec_bg, spec_data,
-                     np * (int64_t)Fa);
-    c->launches++;
-    TC_TRY(dev_sum_threshold(c, np, 1, Fa, 1, spec_data, spec_data, spec_fl, spec_fl, nullptr,
+                            p->background_reject, slo, shi, nchunks, smax, spec_bg, spec_res, spec_data));
+    TC_TRY(dev_sum_threshold(c, np, 1, Fa, 1, spec_res, spec_res, spec_fl, spec_fl, nullptr,
                              p->windows_freq, p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
                              p->freq_chunk_ends, nce, spec_out));
     // flags |= spec_flags (flagging.py:954), both layouts
@@ -290,14 +302,11 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_TRY(tc_alloc(c, N, &bg_FT)); TC_TRY(tc_alloc(c, N, &dres_TF));
     int64_t *rlo, *rhi, rmax;
     TC_TRY(dev_make_ranges(c, np, T, Fa, p->freq_chunk_ends, nce, &rlo, &rhi, &rmax));
+    // background and data -= background (flagging.py:957-962), in both layouts
     TC_TRY(dev_background2d(c, np, T, Fa, data_TF, data_FT, fl_TF, fl_FT, iters, p->radii_2d,
-                            p->background_reject, rlo, rhi, nchunks, rmax, bg_FT));
-    // data -= background (flagging.py:962), in both layouts
-    TC_LAUNCH_NOSYNC(k_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, bg_FT, bg_FT, N);
-    c->launches++;
-    TC_KERNEL_CHECK();
+                            p->background_reject, rlo, rhi, nchunks, rmax, bg_FT, dres_TF, data_TF));
     float *dres_FT = bg_FT;
-    TC_TRY(launch_transpose<float>(c, dres_FT, dres_TF, np, Fa, T));
+    TC_TRY(launch_transpose<float>(c, dres_TF, dres_FT, np, T, Fa));
 
     // SumThreshold along time (flagging.py:964-965)
     u8 *time_TF, *freq_FT, *freq_TF;

@@ -629,10 +629,10 @@ int tc_stage_interp_nans(tc_context *c, const float *data, int64_t ncp, int64_t 
     TC_TRY(tc_stage_in(c, data, (size_t)n, space, &din));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)n, space, &dout));
     if (n) {
-        TC_CUDA(cudaMemcpyAsync(dout, din, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-        // TF layout: line (cp, t) is contiguous
-        TC_LAUNCH_NOSYNC(k_interp_nans, tc_blocks_for(ncp * T, 128), 128, 0, c->stream, dout, ncp * T, (int64_t)1,
-                         F, (int64_t)0, (int)F, (int64_t)1);
+        int *rv;
+        TC_TRY(tc_alloc(c, (size_t)n, &rv));
+        TC_LAUNCH(k_interp_nans_rows, tc_blocks_for(ncp * T * 32, 128), 128, 0, c->stream, din,
+                  (const float *)nullptr, dout, rv, ncp * T, (int)F);
         c->launches++;
         TC_KERNEL_CHECK();
     }
@@ -653,11 +653,9 @@ int tc_stage_background2d(tc_context *c, const float *data, const uint8_t *flags
     float *o_FT, *o_TF;
     TC_TRY(tc_alloc(c, (size_t)n, &o_FT));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)n, space, &o_TF));
-    if (n) {
+    if (n)
         TC_TRY(dev_background2d(c, ncp, (int)T, (int)F, s.d_TF, s.d_FT, s.f_TF, s.f_FT, iterations, radii,
-                                reject_threshold, lo, hi, nce - 1, mr, o_FT));
-        TC_TRY(launch_transpose<float>(c, o_FT, o_TF, ncp, (int)F, (int)T));
-    }
+                                reject_threshold, lo, hi, nce - 1, mr, o_FT, o_TF, nullptr));
     return tc_stage_out_end(c, out, o_TF, (size_t)n, space);
 }
 

@@ -103,33 +103,41 @@ __global__ void k_box_filter(FilterArgs a)
         float y = 0.f;
         float *rp = ring + lane;
         float *const rend = ring + (size_t)L * 32 + lane;
-        // three rotating input buffers: loads run two groups (16 ticks) ahead
+        // three rotating input buffers: loads run two groups (16 ticks) ahead.
+        // The registers hold the RAW loaded words; nothing may depend on them
+        // until the group is consumed, or the prefetch degenerates into a stall.
         float x0[TC_FILT_U], x1[TC_FILT_U], x2[TC_FILT_U];
+        unsigned f0[TC_FILT_U], f1[TC_FILT_U], f2[TC_FILT_U];
 
-#define TC_FILT_LOADG(X, T0)                                                           \
+#define TC_FILT_LOADG(X, FX, T0)                                                       \
         _Pragma("unroll")                                                              \
         for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                       \
             const int m_ = (T0) + k_;                                                  \
             X[k_] = 0.f;                                                               \
+            FX[k_] = 1u;                                                               \
             if (loader && m_ < n) {                                                    \
                 const int64_t off_ = (int64_t)m_ * nj;                                 \
                 if (MODE_IN == FIN_MASKED) {                                           \
-                    const bool fl_ = pfl[off_] != 0;                                   \
-                    if (arr == 0) { const float d_ = pin[off_]; X[k_] = fl_ ? 0.f : d_; } \
-                    else X[k_] = fl_ ? 0.f : 1.f;                                      \
+                    FX[k_] = pfl[off_];                                                \
+                    if (arr == 0) X[k_] = pin[off_];                                   \
                 } else {                                                               \
+                    FX[k_] = 0u;                                                       \
                     X[k_] = pin[off_];                                                 \
                 }                                                                      \
             }                                                                          \
         }
 
-#define TC_FILT_GROUP(X, T0)                                                           \
+// value of a raw (sample, flag) pair for this lane's array
+#define TC_FILT_VALUE(XV, FV)                                                          \
+        (MODE_IN == FIN_MASKED ? ((FV) != 0u ? 0.f : (arr == 0 ? (XV) : 1.f)) : (XV))
+
+#define TC_FILT_GROUP(X, FX, T0)                                                           \
         {                                                                              \
             _Pragma("unroll")                                                          \
             for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                   \
                 const int m_ = (T0) + k_ - pass;                                       \
                 const float prev_ = __shfl_up_sync(TC_FULL_MASK, y, 8);                \
-                const float uin_ = pass == 0 ? X[k_] : prev_;                          \
+                const float uin_ = pass == 0 ? TC_FILT_VALUE(X[k_], FX[k_]) : prev_;                          \
                 const float u_ = (m_ >= add_lo && m_ < add_hi) ? uin_ : 0.f;           \
                 const float old_ = (m_ >= r2) ? *rp : 0.f;                             \
                 *rp = u_;                                                              \
@@ -157,20 +165,21 @@ __global__ void k_box_filter(FilterArgs a)
             __syncwarp();                                                              \
         }
 
-        TC_FILT_LOADG(x0, 0)
-        TC_FILT_LOADG(x1, TC_FILT_U)
+        TC_FILT_LOADG(x0, f0, 0)
+        TC_FILT_LOADG(x1, f1, TC_FILT_U)
         for (int t0 = 0; t0 < nticks; t0 += 3 * TC_FILT_U) {
-            TC_FILT_LOADG(x2, t0 + 2 * TC_FILT_U)
-            TC_FILT_GROUP(x0, t0)
+            TC_FILT_LOADG(x2, f2, t0 + 2 * TC_FILT_U)
+            TC_FILT_GROUP(x0, f0, t0)
             if (t0 + TC_FILT_U >= nticks) break;
-            TC_FILT_LOADG(x0, t0 + 3 * TC_FILT_U)
-            TC_FILT_GROUP(x1, t0 + TC_FILT_U)
+            TC_FILT_LOADG(x0, f0, t0 + 3 * TC_FILT_U)
+            TC_FILT_GROUP(x1, f1, t0 + TC_FILT_U)
             if (t0 + 2 * TC_FILT_U >= nticks) break;
-            TC_FILT_LOADG(x1, t0 + 4 * TC_FILT_U)
-            TC_FILT_GROUP(x2, t0 + 2 * TC_FILT_U)
+            TC_FILT_LOADG(x1, f1, t0 + 4 * TC_FILT_U)
+            TC_FILT_GROUP(x2, f2, t0 + 2 * TC_FILT_U)
         }
 #undef TC_FILT_LOADG
 #undef TC_FILT_GROUP
+#undef TC_FILT_VALUE
     }
 }
 

@@ -64,6 +64,9 @@ struct FilterArgs {
 // Pass-0 lanes fetch the input one group (8 ticks) ahead; pass-3 lanes park
 // their outputs in a small staging tile that all 32 lanes drain every 8 ticks
 // (division by d^4, background = value / weight, coalesced 16-byte stores).
+// shared memory per warp: [staging tile 64][input tiles 2 x 64][ring L x 32] floats
+#define TC_FILT_WARP_FIXED 192
+
 template <bool SMEM_RING, int MODE_IN, int MODE_OUT>
 __global__ void k_box_filter(FilterArgs a)
 {
@@ -71,115 +74,127 @@ __global__ void k_box_filter(FilterArgs a)
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;            // warp in block
     const int nwb = blockDim.x >> 5;
-    const int pass = lane >> 3, arr = (lane >> 2) & 1, q = lane & 3;
+    const int pass = lane >> 3;
     const int L = 2 * a.r, r2 = 2 * a.r, r4 = 4 * a.r;
     const int n = a.n;
     const int64_t nj = a.nj;
     const int64_t ngroups = (a.nlines + TC_FILT_LPW - 1) / TC_FILT_LPW;
     const int64_t gwarp = (int64_t)blockIdx.x * nwb + wib;
     const int64_t nwarps = (int64_t)gridDim.x * nwb;
-    // per-warp shared memory: staging tile [8 ticks][8 outputs] then the ring [L][32]
-    float *stg = smem + (size_t)wib * (64 + (SMEM_RING ? (size_t)L * 32 : 0));
-    float *ring = SMEM_RING ? (stg + 64) : (a.gring + (size_t)gwarp * L * 32);
+    float *stg = smem + (size_t)wib * (TC_FILT_WARP_FIXED + (SMEM_RING ? (size_t)L * 32 : 0));
+    float *tile = stg + 64;                      // 2 x [8 ticks][2 arrays x 4 lines]
+    float *ring = SMEM_RING ? (stg + TC_FILT_WARP_FIXED) : (a.gring + (size_t)gwarp * L * 32);
     const int nticks = n + r4 + 3;
     // window of local ticks in which this pass really receives a sample
     const int add_lo = pass == 3 ? r2 : 0;
     const int add_hi = pass == 0 ? n : (pass == 1 ? n + r2 : 0x7fffffff);
-    const int kk = lane >> 2, qq = lane & 3;     // drain role: (tick in group, line)
+    // load / drain role of this lane: tick kk of a group, line qq of the warp
+    const int kk = lane >> 2, qq = lane & 3;
 
     for (int64_t grp = gwarp; grp < ngroups; grp += nwarps) {
-        const int64_t line = grp * TC_FILT_LPW + q;
-        const bool line_ok = line < a.nlines;
-        const int64_t plane = line_ok ? line / nj : 0;
-        const int64_t base = line_ok ? plane * (int64_t)n * nj + (line - plane * nj) : 0;
-        const bool loader = pass == 0 && line_ok;
         const int64_t oline = grp * TC_FILT_LPW + qq;
         const bool oline_ok = oline < a.nlines;
         const int64_t oplane = oline_ok ? oline / nj : 0;
         const int64_t obase = oline_ok ? oplane * (int64_t)n * nj + (oline - oplane * nj) : 0;
-        const float *pin = (MODE_IN == FIN_PAIR && arr == 1) ? a.win + base : a.data + base;
-        const u8 *pfl = MODE_IN == FIN_MASKED ? a.flags + base : nullptr;
         double s = 0.0;
         float y = 0.f;
         float *rp = ring + lane;
         float *const rend = ring + (size_t)L * 32 + lane;
-        // three rotating input buffers: loads run two groups (16 ticks) ahead.
-        // The registers hold the RAW loaded words; nothing may depend on them
-        // until the group is consumed, or the prefetch degenerates into a stall.
-        float x0[TC_FILT_U], x1[TC_FILT_U], x2[TC_FILT_U];
-        unsigned f0[TC_FILT_U], f1[TC_FILT_U], f2[TC_FILT_U];
+        float ra = 0.f, rb = 0.f;     // raw words of the two in-flight input groups
+        unsigned fa = 1u, fb = 1u;
+        float wa = 0.f, wb = 0.f;
 
-#define TC_FILT_LOADG(X, FX, T0)                                                       \
-        _Pragma("unroll")                                                              \
-        for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                       \
-            const int m_ = (T0) + k_;                                                  \
-            X[k_] = 0.f;                                                               \
-            FX[k_] = 1u;                                                               \
-            if (loader && m_ < n) {                                                    \
-                const int64_t off_ = (int64_t)m_ * nj;                                 \
-                if (MODE_IN == FIN_MASKED) {                                           \
-                    FX[k_] = pfl[off_];                                                \
-                    if (arr == 0) X[k_] = pin[off_];                                   \
-                } else {                                                               \
-                    FX[k_] = 0u;                                                       \
-                    X[k_] = pin[off_];                                                 \
-                }                                                                      \
+// fetch this lane's sample of the group starting at tick T0 (raw words only:
+// nothing may depend on them until TC_FILT_PUBLISH)
+#define TC_FILT_FETCH(R, F, W, T0)                                                     \
+        {                                                                              \
+            const int m_ = (T0) + kk;                                                  \
+            R = 0.f; F = 1u; W = 0.f;                                                  \
+            if (oline_ok && m_ < n) {                                                  \
+                const int64_t idx_ = obase + (int64_t)m_ * nj;                         \
+                R = a.data[idx_];                                                      \
+                if (MODE_IN == FIN_MASKED) F = a.flags[idx_];                          \
+                else { F = 0u; W = a.win[idx_]; }                                      \
             }                                                                          \
         }
-
-// value of a raw (sample, flag) pair for this lane's array
-#define TC_FILT_VALUE(XV, FV)                                                          \
-        (MODE_IN == FIN_MASKED ? ((FV) != 0u ? 0.f : (arr == 0 ? (XV) : 1.f)) : (XV))
-
-#define TC_FILT_GROUP(X, FX, T0)                                                           \
+// turn the raw words into (value, weight) and publish them in input tile B
+#define TC_FILT_PUBLISH(R, F, W, B)                                                    \
         {                                                                              \
-            _Pragma("unroll")                                                          \
-            for (int k_ = 0; k_ < TC_FILT_U; k_++) {                                   \
-                const int m_ = (T0) + k_ - pass;                                       \
-                const float prev_ = __shfl_up_sync(TC_FULL_MASK, y, 8);                \
-                const float uin_ = pass == 0 ? TC_FILT_VALUE(X[k_], FX[k_]) : prev_;                          \
-                const float u_ = (m_ >= add_lo && m_ < add_hi) ? uin_ : 0.f;           \
-                const float old_ = (m_ >= r2) ? *rp : 0.f;                             \
-                *rp = u_;                                                              \
-                s += (double)u_;                                                       \
-                y = (float)s;                                                          \
-                s -= (double)old_;                                                     \
-                if (pass == 3) stg[k_ * 8 + (lane - 24)] = y;                          \
-                rp += 32;                                                              \
-                if (rp == rend) rp = ring + lane;                                      \
+            float v_, w_;                                                              \
+            if (MODE_IN == FIN_MASKED) { v_ = F ? 0.f : R; w_ = F ? 0.f : 1.f; }       \
+            else { v_ = R; w_ = W; }                                                   \
+            tile[(B) * 64 + kk * 8 + qq] = v_;                                         \
+            tile[(B) * 64 + kk * 8 + 4 + qq] = w_;                                     \
+        }
+// one tick of every lane's pass; FAST drops the warm-up / run-out predicates
+#define TC_FILT_TICK(K, T0, B, FAST)                                                   \
+        {                                                                              \
+            const float prev_ = __shfl_up_sync(TC_FULL_MASK, y, 8);                    \
+            float u_ = prev_;                                                          \
+            if (pass == 0) u_ = tile[(B) * 64 + (K) * 8 + lane];                       \
+            float old_;                                                                \
+            if (FAST) {                                                                \
+                old_ = *rp;                                                            \
+            } else {                                                                   \
+                const int m_ = (T0) + (K) - pass;                                      \
+                u_ = (m_ >= add_lo && m_ < add_hi) ? u_ : 0.f;                         \
+                old_ = (m_ >= r2) ? *rp : 0.f;                                         \
+            }                                                                          \
+            *rp = u_;                                                                  \
+            s += (double)u_;                                                           \
+            y = (float)s;                                                              \
+            s -= (double)old_;                                                         \
+            if (pass == 3) stg[(K) * 8 + (lane - 24)] = y;                             \
+            rp += 32;                                                                  \
+            if (rp == rend) rp = ring + lane;                                          \
+        }
+// one group: publish the group fetched last iteration, fetch the one after,
+// run 8 ticks, drain 32 outputs
+#define TC_FILT_ITER(T0, B, RN, FN, WN, RP, FP, WP)                                    \
+        {                                                                              \
+            TC_FILT_PUBLISH(RP, FP, WP, (B) ^ 1)                                       \
+            TC_FILT_FETCH(RN, FN, WN, (T0) + 2 * TC_FILT_U)                            \
+            const int jout_ = (T0) + kk - 3 - r4;                                      \
+            const bool out_ok_ = jout_ >= 0 && jout_ < n && oline_ok;                  \
+            const int64_t oidx_ = obase + (int64_t)(out_ok_ ? jout_ : 0) * nj;         \
+            float d2_ = 0.f;                                                           \
+            if (MODE_OUT == FOUT_RESID && out_ok_) d2_ = a.data2[oidx_];               \
+            __syncwarp();                                                              \
+            if ((T0) - 3 >= r2 && (T0) + TC_FILT_U <= n) {                             \
+                _Pragma("unroll")                                                      \
+                for (int k_ = 0; k_ < TC_FILT_U; k_++) TC_FILT_TICK(k_, T0, B, true)   \
+            } else {                                                                   \
+                _Pragma("unroll")                                                      \
+                for (int k_ = 0; k_ < TC_FILT_U; k_++) TC_FILT_TICK(k_, T0, B, false)  \
             }                                                                          \
             __syncwarp();                                                              \
-            const int jout_ = (T0) + kk - 3 - r4;                                      \
-            if (jout_ >= 0 && jout_ < n && oline_ok) {                                 \
-                const int64_t idx_ = obase + (int64_t)jout_ * nj;                      \
+            if (out_ok_) {                                                             \
                 const float fv_ = stg[kk * 8 + qq] / a.div, fw_ = stg[kk * 8 + 4 + qq] / a.div; \
                 if (MODE_OUT == FOUT_PAIR) {                                           \
-                    a.vout[idx_] = fv_;                                                \
-                    a.wout[idx_] = fw_;                                                \
+                    a.vout[oidx_] = fv_;                                               \
+                    a.wout[oidx_] = fw_;                                               \
                 } else {                                                               \
                     float bg_ = (fw_ == 0.f) ? NAN : fv_ / fw_;                        \
-                    if (MODE_OUT == FOUT_RESID) bg_ = fabsf(a.data2[idx_] - bg_);      \
-                    a.vout[idx_] = bg_;                                                \
+                    if (MODE_OUT == FOUT_RESID) bg_ = fabsf(d2_ - bg_);                \
+                    a.vout[oidx_] = bg_;                                               \
                 }                                                                      \
             }                                                                          \
-            __syncwarp();                                                              \
         }
 
-        TC_FILT_LOADG(x0, f0, 0)
-        TC_FILT_LOADG(x1, f1, TC_FILT_U)
-        for (int t0 = 0; t0 < nticks; t0 += 3 * TC_FILT_U) {
-            TC_FILT_LOADG(x2, f2, t0 + 2 * TC_FILT_U)
-            TC_FILT_GROUP(x0, f0, t0)
+        // prologue: group 0 goes straight into tile 0, group 1 stays in flight
+        TC_FILT_FETCH(ra, fa, wa, 0)
+        TC_FILT_PUBLISH(ra, fa, wa, 0)
+        TC_FILT_FETCH(rb, fb, wb, TC_FILT_U)
+        for (int t0 = 0; t0 < nticks; t0 += 2 * TC_FILT_U) {
+            TC_FILT_ITER(t0, 0, ra, fa, wa, rb, fb, wb)
             if (t0 + TC_FILT_U >= nticks) break;
-            TC_FILT_LOADG(x0, f0, t0 + 3 * TC_FILT_U)
-            TC_FILT_GROUP(x1, f1, t0 + TC_FILT_U)
-            if (t0 + 2 * TC_FILT_U >= nticks) break;
-            TC_FILT_LOADG(x1, f1, t0 + 4 * TC_FILT_U)
-            TC_FILT_GROUP(x2, f2, t0 + 2 * TC_FILT_U)
+            TC_FILT_ITER(t0 + TC_FILT_U, 1, rb, fb, wb, ra, fa, wa)
         }
-#undef TC_FILT_LOADG
-#undef TC_FILT_GROUP
-#undef TC_FILT_VALUE
+        __syncwarp();
+#undef TC_FILT_FETCH
+#undef TC_FILT_PUBLISH
+#undef TC_FILT_TICK
+#undef TC_FILT_ITER
     }
 }
 
@@ -233,7 +248,7 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
     a.div = tc_f32_pow4(2 * (int64_t)a.r + 1);
     tc_prof_begin(c, TCP_BOX_FILTER);
     const int64_t ngroups = (a.nlines + TC_FILT_LPW - 1) / TC_FILT_LPW;
-    const size_t per_warp = ((size_t)2 * a.r * 32 + 64) * sizeof(float);
+    const size_t per_warp = ((size_t)2 * a.r * 32 + TC_FILT_WARP_FIXED) * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;
     if (per_warp <= smem_cap) {
         // 4 warps (16 lines) per block unless the delay lines are too deep
@@ -252,7 +267,7 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
         TC_TRY(tc_alloc(c, (size_t)blocks * wpb * 2 * a.r * 32, &g));
         a.gring = g;
         a.gring_stride = 0;
-        TC_TRY(launch_box_filter_mode<false>(c, a, (unsigned)blocks, wpb * 32, 64 * sizeof(float) * wpb));
+        TC_TRY(launch_box_filter_mode<false>(c, a, (unsigned)blocks, wpb * 32, TC_FILT_WARP_FIXED * sizeof(float) * wpb));
     }
     tc_prof_end(c);
     c->launches++;

@@ -209,6 +209,78 @@ struct StScanArgs {
     u8 *pn;                   // [nplanes][nchunks][mpad][ninner]
 };
 
+// One SumThreshold window over a padded chunk.  The prefix values that the
+// window sums need (cum[i+1-w]) are kept in a w-deep register ring when w is
+// 1, 2, 4 or 8 (every default.yaml time window and all but one frequency
+// list); other widths spill the prefix to the coalesced global scratch.
+template <int W>
+__device__ __forceinline__ void st_window_reg(const float *d, u8 *pn, int m, int64_t es, int64_t ss,
+                                              double limit, double sc, double nsc)
+{
+    double h[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) h[k] = 0.0;
+    double c = 0.0;
+    int lastpos = -(1 << 30), lastneg = -(1 << 30);
+    for (int i0 = 0; i0 < m; i0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + k;
+            if (i < m) {
+                double x = (double)d[(int64_t)i * es];
+                const u8 st = pn[(int64_t)i * ss];
+                if ((st & 1) && x > limit) x = limit;
+                else if ((st & 2) && x < -limit) x = -limit;
+                c = c + x;
+                const int j = i + 1 - W;
+                const double cj = h[k % W];  // cum[j] (0 for j == 0)
+                h[k % W] = c;
+                if (j >= 0) {
+                    const double avg = c - cj;
+                    if (avg * sc > limit) lastpos = j;
+                    if (avg * nsc > limit) lastneg = j;
+                    const u8 add = (u8)(((j - lastpos < W) ? 1 : 0) | ((j - lastneg < W) ? 2 : 0));
+                    if (add) pn[(int64_t)j * ss] |= add;
+                }
+            }
+        }
+    }
+    int jt = m - W + 1; if (jt < 0) jt = 0;
+    for (int j = jt; j < m; j++) {
+        const u8 add = (u8)(((j - lastpos < W) ? 1 : 0) | ((j - lastneg < W) ? 2 : 0));
+        if (add) pn[(int64_t)j * ss] |= add;
+    }
+}
+
+__device__ __forceinline__ void st_window_mem(const float *d, u8 *pn, double *cum, int m, int w, int64_t es,
+                                              int64_t ss, double limit, double sc, double nsc)
+{
+    double c = 0.0;
+    cum[0] = 0.0;
+    int lastpos = -(1 << 30), lastneg = -(1 << 30);
+    for (int i = 0; i < m; i++) {
+        double x = (double)d[(int64_t)i * es];
+        const u8 st = pn[(int64_t)i * ss];
+        if ((st & 1) && x > limit) x = limit;
+        else if ((st & 2) && x < -limit) x = -limit;
+        c = c + x;
+        cum[(int64_t)(i + 1) * ss] = c;
+        const int j = i + 1 - w;
+        if (j >= 0) {
+            const double avg = c - cum[(int64_t)j * ss];
+            if (avg * sc > limit) lastpos = j;
+            if (avg * nsc > limit) lastneg = j;
+            const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+            if (add) pn[(int64_t)j * ss] |= add;
+        }
+    }
+    int jt = m - w + 1; if (jt < 0) jt = 0;
+    for (int j = jt; j < m; j++) {
+        const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+        if (add) pn[(int64_t)j * ss] |= add;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_st_scan(StScanArgs a)
 {
@@ -240,30 +312,11 @@ k_st_scan(StScanArgs a)
         const double limit = (double)thr / a.tf[wi];
         const double sc = (double)a.scale[wi];
         const double nsc = (double)(-a.scale[wi]);
-        double c = 0.0;
-        cum[0] = 0.0;
-        int lastpos = -(1 << 30), lastneg = -(1 << 30);
-        for (int i = 0; i < m; i++) {
-            double x = (double)d[(int64_t)i * es];
-            u8 st = pn[(int64_t)i * ss];
-            if ((st & 1) && x > limit) x = limit;
-            else if ((st & 2) && x < -limit) x = -limit;
-            c = c + x;
-            cum[(int64_t)(i + 1) * ss] = c;
-            int j = i + 1 - w;
-            if (j >= 0) {
-                double avg = c - cum[(int64_t)j * ss];
-                if (avg * sc > limit) lastpos = j;
-                if (avg * nsc > limit) lastneg = j;
-                u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-                if (add) pn[(int64_t)j * ss] |= add;
-            }
-        }
-        int jt = m - w + 1; if (jt < 0) jt = 0;
-        for (int j = jt; j < m; j++) {
-            u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-            if (add) pn[(int64_t)j * ss] |= add;
-        }
+        if (w == 1) st_window_reg<1>(d, pn, m, es, ss, limit, sc, nsc);
+        else if (w == 2) st_window_reg<2>(d, pn, m, es, ss, limit, sc, nsc);
+        else if (w == 4) st_window_reg<4>(d, pn, m, es, ss, limit, sc, nsc);
+        else if (w == 8) st_window_reg<8>(d, pn, m, es, ss, limit, sc, nsc);
+        else st_window_mem(d, pn, cum, m, w, es, ss, limit, sc, nsc);
     }
     int rel = c0 - p0;
     for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = pn[(int64_t)(rel + i) * ss] ? 1 : 0;

@@ -275,6 +275,8 @@ struct ChunkSelectArgs {
     float uv_sigma;
     int uv_replace;           // 1: flags = new, 0: flags |= new
     const int *uv_unflagged;  // [nranges] number of unflagged samples (0 -> plane skipped)
+    const unsigned *todo;     // optional [nranges]: the sliced radix kernels only touch ranges with todo != 0
+    double *medbuf;           // [nranges] where the sliced paths leave the median for k_sel_update
 };
 
 #define TC_SEL_BINS 2048
@@ -421,6 +423,7 @@ k_sel_hist(ChunkSelectArgs a, const SelState *__restrict__ st, uint32_t *__restr
 {
     __shared__ uint32_t hist[TC_SEL_BINS];
     const int range = blockIdx.y;
+    if (a.todo && !a.todo[range]) return;
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
     int64_t hi = lo + TC_SEL_SLICE;
     if (hi > a.range_hi[range]) hi = a.range_hi[range];
@@ -458,11 +461,12 @@ k_sel_hist(ChunkSelectArgs a, const SelState *__restrict__ st, uint32_t *__restr
 
 // one block per range: find the digit holding the wanted rank, clear the histogram
 __global__ void __launch_bounds__(256)
-k_sel_pick(SelState *__restrict__ st, uint32_t *__restrict__ ghist, int pass)
+k_sel_pick(SelState *__restrict__ st, uint32_t *__restrict__ ghist, int pass, const unsigned *__restrict__ todo)
 {
     __shared__ uint32_t part[256];
     __shared__ uint32_t s_digit, s_acc;
     const int range = blockIdx.x, tid = threadIdx.x;
+    if (todo && !todo[range]) return;
     uint32_t *gh = ghist + (size_t)range * TC_SEL_BINS;
     const int per = TC_SEL_BINS / 256;
     uint32_t loc[TC_SEL_BINS / 256];
@@ -506,6 +510,7 @@ __global__ void __launch_bounds__(1024)
 k_sel_lower(ChunkSelectArgs a, SelState *__restrict__ st)
 {
     const int range = blockIdx.y;
+    if (a.todo && !a.todo[range]) return;
     const SelState s = st[range];
     if (s.total == 0 || (s.total & 1u) || s.remaining != 0) return;
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
@@ -529,6 +534,7 @@ k_sel_finish(ChunkSelectArgs a, SelState *__restrict__ st, int nranges)
 {
     int range = blockIdx.x * blockDim.x + threadIdx.x;
     if (range >= nranges) return;
+    if (a.todo && !a.todo[range]) return;
     SelState s = st[range];
     double med = NAN;
     if (s.total > 0) {
@@ -537,17 +543,18 @@ k_sel_finish(ChunkSelectArgs a, SelState *__restrict__ st, int nranges)
         med = median_from_pair(lower, upper, (int)s.total);
     }
     st[range].med = med;
+    if (a.medbuf) a.medbuf[range] = med;
     if (a.medians) a.medians[range] = med;
 }
 
 __global__ void __launch_bounds__(1024)
-k_sel_update(ChunkSelectArgs a, const SelState *__restrict__ st)
+k_sel_update(ChunkSelectArgs a)
 {
     const int range = blockIdx.y;
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
     int64_t hi = lo + TC_SEL_SLICE;
     if (hi > a.range_hi[range]) hi = a.range_hi[range];
-    const double med = st[range].med;
+    const double med = a.medbuf[range];
     if (a.mode == CS_BACKGROUND) {
         double thr = med * a.thr_mult;
         if (thr != thr) return;
@@ -564,11 +571,14 @@ k_sel_update(ChunkSelectArgs a, const SelState *__restrict__ st)
     }
 }
 
-static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a, int64_t nranges, int64_t max_range)
+static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in, int64_t nranges, int64_t max_range,
+                                     bool with_update = true)
 {
     tc_mark mark = tc_arena_mark(c);
     SelState *st;
     uint32_t *gh;
+    ChunkSelectArgs a = a_in;
+    if (!a.medbuf) TC_TRY(tc_alloc(c, (size_t)nranges, &a.medbuf));
     TC_TRY(tc_alloc(c, (size_t)nranges, &st));
     TC_TRY(tc_alloc(c, (size_t)nranges * TC_SEL_BINS, &gh));
     TC_CUDA(cudaMemsetAsync(gh, 0, sizeof(uint32_t) * (size_t)nranges * TC_SEL_BINS, c->stream));
@@ -581,16 +591,18 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a, in
         if (b.sub) b.sub += r0;
         if (b.medians) b.medians += r0;
         if (b.uv_unflagged) b.uv_unflagged += r0;
+        if (b.todo) b.todo += r0;
+        b.medbuf += r0;
         dim3 grid(slices, nr);
         for (int pass = 0; pass < 3; pass++) {
             TC_LAUNCH(k_sel_hist, grid, 1024, 0, c->stream, b, st + r0, gh + r0 * TC_SEL_BINS, pass);
-            TC_LAUNCH(k_sel_pick, nr, 256, 0, c->stream, st + r0, gh + r0 * TC_SEL_BINS, pass);
+            TC_LAUNCH(k_sel_pick, nr, 256, 0, c->stream, st + r0, gh + r0 * TC_SEL_BINS, pass, b.todo);
         }
         TC_LAUNCH(k_sel_lower, grid, 1024, 0, c->stream, b, st + r0);
         TC_LAUNCH_NOSYNC(k_sel_finish, tc_blocks_for(nr, 128), 128, 0, c->stream, b, st + r0, (int)nr);
         c->launches += 8;
-        if (a.mode != CS_REPORT) {
-            TC_LAUNCH_NOSYNC(k_sel_update, grid, 1024, 0, c->stream, b, st + r0);
+        if (a.mode != CS_REPORT && with_update) {
+            TC_LAUNCH_NOSYNC(k_sel_update, grid, 1024, 0, c->stream, b);
             c->launches++;
         }
     }
@@ -600,10 +612,289 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a, in
     return TC_OK;
 }
 
+// ----------------------------------------------------------------------------
+// Bracket select: the exact median in two sweeps over the data instead of four.
+//   1. k_brk_sample   a stratified sample of 2048 keys per range is sorted in
+//                     shared memory; keys at sample ranks mid -+ delta bracket
+//                     the true median with overwhelming probability.  Ranges
+//                     of at most 2048 samples are sorted outright (exact).
+//   2. k_brk_collect  one sweep: count the keys below the bracket, copy the keys
+//                     inside it (a few percent) to a compact buffer.
+//   3. k_brk_select   radix select of rank (n/2 - below) inside the compact
+//                     buffer; it also yields the lower middle key for even n.
+//   4. ranges whose bracket missed (or overflowed the buffer) are redone by the
+//      sliced radix select; k_sel_update applies the thresholds.
+// The result is the same exact order statistic; only the visiting order differs.
+// ----------------------------------------------------------------------------
+#define TC_BRK_SAMPLES 2048
+
+struct BrkState {
+    uint32_t lo, hi;        // bracket keys (inclusive)
+    uint32_t n_valid, n_below, n_in;
+    uint32_t done;          // median already final
+    uint32_t pad0, pad1;
+};
+
+__device__ __forceinline__ uint32_t brk_hash(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo)
+{
+    __shared__ uint32_t keys[TC_BRK_SAMPLES];
+    __shared__ int s_valid;
+    const int range = blockIdx.x, tid = threadIdx.x;
+    const int64_t lo = a.range_lo[range], hi = a.range_hi[range];
+    const int64_t len = hi - lo;
+    const float sub = a.sub ? (float)a.sub[range] : 0.0f;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    const bool exact = len <= TC_BRK_SAMPLES;
+    int nv = 0;
+    for (int j = tid; j < TC_BRK_SAMPLES; j += 256) {
+        uint32_t k = 0xffffffffu;
+        int64_t pos = -1;
+        if (exact) { if (j < len) pos = lo + j; }
+        else {
+            // stratified: one sample per stratum of len / 2048 elements
+            int64_t s0 = (int64_t)j * len / TC_BRK_SAMPLES, s1 = (int64_t)(j + 1) * len / TC_BRK_SAMPLES;
+            int64_t w = s1 - s0 > 0 ? s1 - s0 : 1;
+            pos = lo + s0 + (int64_t)(brk_hash((uint32_t)j * 2654435761u ^ (uint32_t)range) % (uint32_t)w);
+        }
+        if (pos >= 0 && !a.flags[pos]) {
+            float x = cs_value(a, pos, sub);
+            if (!(a.skip_nan && x != x)) { k = f2key(x); nv++; }
+        }
+        keys[j] = k;
+    }
+    atomicAdd(&s_valid, nv);
+    __syncthreads();
+    // bitonic sort of 2048 keys (invalid keys = 0xffffffff sink to the end)
+    for (int size = 2; size <= TC_BRK_SAMPLES; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < TC_BRK_SAMPLES / 2; t += 256) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                bool up = (i & size) == 0;
+                uint32_t x = keys[i], y = keys[j];
+                if ((x > y) == up) { keys[i] = y; keys[j] = x; }
+            }
+            __syncthreads();
+        }
+    if (tid == 0) {
+        const int sv = s_valid;
+        BrkState b;
+        b.lo = 0; b.hi = 0xfffffffeu; b.n_valid = 0; b.n_below = 0; b.n_in = 0; b.done = 0; b.pad0 = b.pad1 = 0;
+        unsigned td = 0;
+        if (exact) {
+            double med = NAN;
+            if (sv > 0) {
+                float upper = key2f(keys[sv >> 1]);
+                float lower = (sv & 1) ? upper : key2f(keys[(sv >> 1) - 1]);
+                med = median_from_pair(lower, upper, sv);
+            }
+            a.medbuf[range] = med;
+            if (a.medians) a.medians[range] = med;
+            b.done = 1;
+            b.n_valid = (uint32_t)sv;
+        } else if (sv >= 64) {
+            int mid = sv >> 1;
+            int delta = (int)(2.5f * sqrtf((float)sv)) + 4;
+            b.lo = mid - delta >= 0 ? keys[mid - delta] : 0u;
+            b.hi = mid + delta < sv ? keys[mid + delta] : 0xfffffffeu;
+        }
+        st[range] = b;
+        todo[range] = td;
+    }
+}
+
+// sweep: count valid / below-bracket keys, copy in-bracket keys to the compact buffer
+__global__ void __launch_bounds__(1024)
+k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap)
+{
+    __shared__ uint32_t s_valid, s_below;
+    const int range = blockIdx.y;
+    if (st[range].done) return;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
+    int64_t hi = lo + TC_SEL_SLICE;
+    if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    if (lo >= hi) return;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const uint32_t klo = st[range].lo, khi = st[range].hi;
+    const float sub = a.sub ? (float)a.sub[range] : 0.0f;
+    uint32_t *out = cbuf + (size_t)range * cap;
+    if (tid == 0) { s_valid = 0; s_below = 0; }
+    __syncthreads();
+    uint32_t nvalid = 0, nbelow = 0;
+    for (int64_t i0 = lo; i0 < hi; i0 += nt) {
+        const int64_t i = i0 + tid;
+        bool in = false;
+        uint32_t k = 0;
+        if (i < hi && !a.flags[i]) {
+            float x = cs_value(a, i, sub);
+            if (!(a.skip_nan && x != x)) {
+                k = f2key(x);
+                nvalid++;
+                if (k < klo) nbelow++;
+                else if (k <= khi) in = true;
+            }
+        }
+        const unsigned m = __ballot_sync(TC_FULL_MASK, in);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == __ffs((int)m) - 1) base = atomicAdd(&st[range].n_in, (uint32_t)__popc(m));
+            base = __shfl_sync(TC_FULL_MASK, base, __ffs((int)m) - 1);
+            if (in) {
+                uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if ((int64_t)slot < cap) out[slot] = k;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(TC_FULL_MASK, nvalid, o);
+        nbelow += __shfl_xor_sync(TC_FULL_MASK, nbelow, o);
+    }
+    if (lane == 0) { atomicAdd(&s_valid, nvalid); atomicAdd(&s_below, nbelow); }
+    __syncthreads();
+    if (tid == 0) { atomicAdd(&st[range].n_valid, s_valid); atomicAdd(&st[range].n_below, s_below); }
+}
+
+// radix select of the wanted rank inside the compact buffer
+__global__ void __launch_bounds__(512)
+k_brk_select(ChunkSelectArgs a, const BrkState *__restrict__ st, const uint32_t *__restrict__ cbuf, int64_t cap,
+             unsigned *__restrict__ todo)
+{
+    __shared__ uint32_t hist[TC_SEL_BINS];
+    __shared__ uint32_t s_prefix, s_remaining, s_best;
+    const int range = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const BrkState b = st[range];
+    if (b.done) return;
+    if (b.n_valid == 0) {
+        if (tid == 0) { a.medbuf[range] = NAN; if (a.medians) a.medians[range] = NAN; }
+        return;
+    }
+    const uint32_t kth = b.n_valid >> 1;
+    const bool even = (b.n_valid & 1u) == 0;
+    // the wanted rank (and, for even counts, a lower neighbour) must lie inside the buffer
+    if ((int64_t)b.n_in > cap || kth < b.n_below || kth >= b.n_below + b.n_in ||
+        (even && kth == b.n_below && b.n_below > 0)) {
+        if (tid == 0) todo[range] = 1;
+        return;
+    }
+    const uint32_t *keys = cbuf + (size_t)range * cap;
+    const uint32_t n = b.n_in;
+    uint32_t prefix = 0, himask = 0, remaining = kth - b.n_below;
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const uint32_t dmask = pass == 2 ? 1023u : 2047u;
+        for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += nt) {
+            uint32_t k = keys[i];
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t rem = remaining, acc = 0, digit = 0;
+            for (uint32_t q = 0; q <= dmask; q++) {
+                if (rem < acc + hist[q]) { digit = q; break; }
+                acc += hist[q];
+            }
+            s_remaining = rem - acc;
+            s_prefix = prefix | (digit << shift);
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        himask |= dmask << shift;
+        __syncthreads();
+    }
+    float upper = key2f(prefix), lower = upper;
+    if (even && remaining == 0) {
+        if (tid == 0) s_best = 0;
+        __syncthreads();
+        uint32_t best = 0;
+        for (uint32_t i = tid; i < n; i += nt) {
+            uint32_t k = keys[i];
+            if (k < prefix && k > best) best = k;
+        }
+        best = warp_max_u(best);
+        if ((tid & 31) == 0 && best) atomicMax(&s_best, best);
+        __syncthreads();
+        lower = key2f(s_best);
+    }
+    if (tid == 0) {
+        double med = median_from_pair(lower, upper, (int)b.n_valid);
+        a.medbuf[range] = med;
+        if (a.medians) a.medians[range] = med;
+    }
+}
+
+static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int64_t nranges, int64_t max_range)
+{
+    tc_mark mark = tc_arena_mark(c);
+    ChunkSelectArgs a = a_in;
+    BrkState *st;
+    unsigned *todo;
+    TC_TRY(tc_alloc(c, (size_t)nranges, &st));
+    TC_TRY(tc_alloc(c, (size_t)nranges, &todo));
+    if (!a.medbuf) TC_TRY(tc_alloc(c, (size_t)nranges, &a.medbuf));
+    const bool small = max_range <= TC_BRK_SAMPLES;
+    const int64_t cap = small ? 1 : max_range / 8 + 4096;
+    uint32_t *cbuf = nullptr;
+    if (!small) TC_TRY(tc_alloc(c, (size_t)nranges * cap, &cbuf));
+    unsigned slices = (unsigned)((max_range + TC_SEL_SLICE - 1) / TC_SEL_SLICE);
+    tc_prof_begin(c, TCP_CHUNK_SELECT);
+    for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
+        unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);
+        ChunkSelectArgs b = a;
+        b.range_lo += r0; b.range_hi += r0;
+        if (b.sub) b.sub += r0;
+        if (b.medians) b.medians += r0;
+        if (b.uv_unflagged) b.uv_unflagged += r0;
+        b.medbuf += r0;
+        TC_LAUNCH(k_brk_sample, nr, 256, 0, c->stream, b, st + r0, todo + r0);
+        c->launches++;
+        if (!small) {
+            TC_LAUNCH(k_brk_collect, dim3(slices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap);
+            TC_LAUNCH(k_brk_select, nr, 512, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap, todo + r0);
+            c->launches += 2;
+        }
+    }
+    tc_prof_end(c);
+    TC_KERNEL_CHECK();
+    if (!small) {
+        // redo the (rare) ranges whose bracket missed with the sliced radix select
+        ChunkSelectArgs f = a;
+        f.todo = todo;
+        TC_TRY(launch_chunk_select_multi(c, f, nranges, max_range, false));
+    }
+    if (a.mode != CS_REPORT) {
+        tc_prof_begin(c, TCP_CHUNK_SELECT);
+        for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
+            unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);
+            ChunkSelectArgs b = a;
+            b.range_lo += r0; b.range_hi += r0;
+            if (b.uv_unflagged) b.uv_unflagged += r0;
+            b.medbuf += r0;
+            TC_LAUNCH_NOSYNC(k_sel_update, dim3(slices, nr), 1024, 0, c->stream, b);
+            c->launches++;
+        }
+        tc_prof_end(c);
+        TC_KERNEL_CHECK();
+    }
+    tc_arena_release(c, mark);
+    return TC_OK;
+}
+
 static int launch_chunk_select(tc_context *c, const ChunkSelectArgs &a, int64_t nranges, int64_t max_range)
 {
     if (nranges == 0) return TC_OK;
-    // long ranges (or too few of them to fill the GPU) go through the sliced path
+    if (!getenv("TC_SELECT_RADIX")) return launch_bracket_select(c, a, nranges, max_range);
+    // reference implementation of the select (kept for A/B checks): plain radix select
     if (max_range > 8 * TC_SEL_SLICE || (max_range > TC_SEL_SLICE && nranges < 2 * (int64_t)c->sm_count))
         return launch_chunk_select_multi(c, a, nranges, max_range);
     int bd = 1024;

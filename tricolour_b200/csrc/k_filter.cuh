@@ -46,6 +46,8 @@ struct FilterArgs {
     float *vout;        // FOUT_PAIR: values; FOUT_BG / FOUT_RESID: background / |data2-bg|
     float *wout;        // FOUT_PAIR: weights
     const float *data2; // FOUT_RESID: the unfiltered samples in the output layout
+    int flags_transposed;  // FIN_MASKED: `flags` is stored (plane, line, sample) instead of (plane, sample, line)
+    int out_transposed;    // outputs are written (plane, line, sample): the layout change is fused into the drain
     float *gring;       // global delay-line scratch (when not in shared memory)
     int64_t gring_stride;
 };
@@ -96,6 +98,8 @@ __global__ void k_box_filter(FilterArgs a)
         const bool oline_ok = oline < a.nlines;
         const int64_t oplane = oline_ok ? oline / nj : 0;
         const int64_t obase = oline_ok ? oplane * (int64_t)n * nj + (oline - oplane * nj) : 0;
+        // same line in the transposed (plane, line, sample) layout
+        const int64_t tbase = oline_ok ? oplane * (int64_t)n * nj + (oline - oplane * nj) * (int64_t)n : 0;
         double s = 0.0;
         float y = 0.f;
         float *rp = ring + lane;
@@ -113,7 +117,7 @@ __global__ void k_box_filter(FilterArgs a)
             if (oline_ok && m_ < n) {                                                  \
                 const int64_t idx_ = obase + (int64_t)m_ * nj;                         \
                 R = a.data[idx_];                                                      \
-                if (MODE_IN == FIN_MASKED) F = a.flags[idx_];                          \
+                if (MODE_IN == FIN_MASKED) F = a.flags[a.flags_transposed ? tbase + m_ : idx_]; \
                 else { F = 0u; W = a.win[idx_]; }                                      \
             }                                                                          \
         }
@@ -156,7 +160,8 @@ __global__ void k_box_filter(FilterArgs a)
             TC_FILT_FETCH(RN, FN, WN, (T0) + 2 * TC_FILT_U)                            \
             const int jout_ = (T0) + kk - 3 - r4;                                      \
             const bool out_ok_ = jout_ >= 0 && jout_ < n && oline_ok;                  \
-            const int64_t oidx_ = obase + (int64_t)(out_ok_ ? jout_ : 0) * nj;         \
+            const int64_t oidx_ = a.out_transposed ? tbase + (out_ok_ ? jout_ : 0)     \
+                                                   : obase + (int64_t)(out_ok_ ? jout_ : 0) * nj; \
             float d2_ = 0.f;                                                           \
             if (MODE_OUT == FOUT_RESID && out_ok_) d2_ = a.data2[oidx_];               \
             __syncwarp();                                                              \

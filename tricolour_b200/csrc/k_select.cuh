@@ -118,6 +118,7 @@ k_line_median(LineMedianArgs a)
     int remaining = kth;
     uint32_t prefix = 0;
     uint32_t cand = valid;  // lanes' candidates whose high bits match `prefix`
+    int ncand = total;
     for (int bit = 31; bit >= 0; bit--) {
         int c0 = 0;
 #pragma unroll
@@ -125,12 +126,22 @@ k_line_median(LineMedianArgs a)
             c0 += ((cand >> k) & 1u) & (((key[k] >> bit) & 1u) ^ 1u);
         c0 = warp_sum_i(c0);
         uint32_t take1 = remaining >= c0 ? 1u : 0u;
-        if (take1) { remaining -= c0; prefix |= 1u << bit; }
+        if (take1) { remaining -= c0; prefix |= 1u << bit; ncand -= c0; }
+        else ncand = c0;
         uint32_t nc = 0;
 #pragma unroll
         for (int k = 0; k < VPL; k++)
             nc |= ((((key[k] >> bit) & 1u) == take1) ? 1u : 0u) << k;
         cand &= nc;
+        if (ncand == 1) {
+            // a single candidate is left: it is the answer (remaining is 0)
+            uint32_t mine = 0;
+#pragma unroll
+            for (int k = 0; k < VPL; k++)
+                if ((cand >> k) & 1u) mine = key[k];
+            prefix = warp_max_u(mine);
+            break;
+        }
     }
     // `prefix` is the key of the upper median; `remaining` its rank among equals
     float upper = key2f(prefix);
@@ -711,11 +722,16 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     }
 }
 
-// sweep: count valid / below-bracket keys, copy in-bracket keys to the compact buffer
+// sweep: count valid / below-bracket keys, copy in-bracket keys to the compact
+// buffer.  In-bracket keys are first gathered in shared memory (one shared
+// atomic per warp and iteration), then the block reserves its share of the
+// range's buffer with ONE global atomic and copies coalesced.
+#define TC_BRK_STAGE 8192
 __global__ void __launch_bounds__(1024)
 k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap)
 {
-    __shared__ uint32_t s_valid, s_below;
+    __shared__ uint32_t stage[TC_BRK_STAGE];
+    __shared__ uint32_t s_valid, s_below, s_in, s_base;
     const int range = blockIdx.y;
     if (st[range].done) return;
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
@@ -726,7 +742,7 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     const uint32_t klo = st[range].lo, khi = st[range].hi;
     const float sub = a.sub ? (float)a.sub[range] : 0.0f;
     uint32_t *out = cbuf + (size_t)range * cap;
-    if (tid == 0) { s_valid = 0; s_below = 0; }
+    if (tid == 0) { s_valid = 0; s_below = 0; s_in = 0; }
     __syncthreads();
     uint32_t nvalid = 0, nbelow = 0;
     for (int64_t i0 = lo; i0 < hi; i0 += nt) {
@@ -745,11 +761,12 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
         const unsigned m = __ballot_sync(TC_FULL_MASK, in);
         if (m) {
             uint32_t base = 0;
-            if (lane == __ffs((int)m) - 1) base = atomicAdd(&st[range].n_in, (uint32_t)__popc(m));
-            base = __shfl_sync(TC_FULL_MASK, base, __ffs((int)m) - 1);
+            const int leader = __ffs((int)m) - 1;
+            if (lane == leader) base = atomicAdd(&s_in, (uint32_t)__popc(m));
+            base = __shfl_sync(TC_FULL_MASK, base, leader);
             if (in) {
                 uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if ((int64_t)slot < cap) out[slot] = k;
+                if (slot < TC_BRK_STAGE) stage[slot] = k;
             }
         }
     }
@@ -759,7 +776,19 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     }
     if (lane == 0) { atomicAdd(&s_valid, nvalid); atomicAdd(&s_below, nbelow); }
     __syncthreads();
-    if (tid == 0) { atomicAdd(&st[range].n_valid, s_valid); atomicAdd(&st[range].n_below, s_below); }
+    if (tid == 0) {
+        atomicAdd(&st[range].n_valid, s_valid);
+        atomicAdd(&st[range].n_below, s_below);
+        // a slice that overflows its stage makes the range's count exceed `cap`,
+        // which sends the range to the radix fallback
+        uint32_t want = s_in <= TC_BRK_STAGE ? s_in : (uint32_t)(cap + 1);
+        s_base = atomicAdd(&st[range].n_in, want);
+    }
+    __syncthreads();
+    const uint32_t cnt = s_in <= TC_BRK_STAGE ? s_in : 0;
+    const uint32_t base = s_base;
+    for (uint32_t q = tid; q < cnt; q += nt)
+        if ((int64_t)(base + q) < cap) out[base + q] = stage[q];
 }
 
 // radix select of the wanted rank inside the compact buffer

@@ -44,18 +44,15 @@ static int dev_make_ranges(tc_context *c, int64_t np, int64_t T, int64_t Fa, con
 }
 
 struct BgWork {
-    u8 *fl_TF, *fl_FT;  // working copy of the flags (gets modified)
-    float *v_TF, *w_TF, *v_FT, *w_FT;
+    u8 *fl_FT;            // working copy of the flags (gets modified), (plane, chan, time)
+    float *v_FT, *w_FT;   // time-filtered value / weight, already in (plane, chan, time)
 };
 
-static int dev_bg_work_alloc(tc_context *c, int64_t N, bool need_tf, BgWork *w)
+static int dev_bg_work_alloc(tc_context *c, int64_t N, bool two_axes, BgWork *w)
 {
     TC_TRY(tc_alloc(c, N, &w->fl_FT));
-    w->fl_TF = nullptr; w->v_TF = w->w_TF = w->v_FT = w->w_FT = nullptr;
-    if (need_tf) {
-        TC_TRY(tc_alloc(c, N, &w->fl_TF));
-        TC_TRY(tc_alloc(c, N, &w->v_TF));
-        TC_TRY(tc_alloc(c, N, &w->w_TF));
+    w->v_FT = w->w_FT = nullptr;
+    if (two_axes) {
         TC_TRY(tc_alloc(c, N, &w->v_FT));
         TC_TRY(tc_alloc(c, N, &w->w_FT));
     }
@@ -80,12 +77,13 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     FilterArgs a;
     memset(&a, 0, sizeof(a));
     if (r0 > 0 && r1 > 0) {
+        // time axis on (T,F) samples; flags are read from, and the outputs written
+        // to, the (F,T) layout directly, so no separate transposes are needed
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
-        a.data = data_TF; a.flags = w.fl_TF; a.vout = w.v_TF; a.wout = w.w_TF;
+        a.data = data_TF; a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
+        a.vout = w.v_FT; a.wout = w.w_FT;
         TC_TRY(launch_box_filter(c, a));
-        TC_TRY(launch_transpose<float>(c, w.v_TF, w.v_FT, np, T, Fa));
-        TC_TRY(launch_transpose<float>(c, w.w_TF, w.w_FT, np, T, Fa));
         memset(&a, 0, sizeof(a));
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
         a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
@@ -94,9 +92,9 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     } else if (r0 > 0) {
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
-        a.data = data_TF; a.flags = w.fl_TF; a.vout = w.v_TF;
+        a.data = data_TF; a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
+        a.vout = out_FT;
         TC_TRY(launch_box_filter(c, a));
-        TC_TRY(launch_transpose<float>(c, w.v_TF, out_FT, np, T, Fa));
         if (resid) {
             TC_LAUNCH_NOSYNC(k_abs_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, out_FT, out_FT, N);
             c->launches++;
@@ -127,14 +125,14 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
                             const float *minuend_TF)
 {
     int64_t N = np * (int64_t)T * Fa;
-    bool need_tf = false;
-    for (int k = 0; k <= iterations; k++) if (radii[2 * k] > 0) need_tf = true;
-    if (T == 1) need_tf = false;
+    bool two_axes = false;
+    for (int k = 0; k <= iterations; k++) if (radii[2 * k] > 0 && radii[2 * k + 1] > 0) two_axes = true;
+    if (T == 1) two_axes = false;
+    (void)flags_TF;
     BgWork w;
     tc_mark mark = tc_arena_mark(c);
-    TC_TRY(dev_bg_work_alloc(c, N, need_tf, &w));
+    TC_TRY(dev_bg_work_alloc(c, N, two_axes, &w));
     TC_CUDA(cudaMemcpyAsync(w.fl_FT, flags_FT, N, cudaMemcpyDeviceToDevice, c->stream));
-    if (need_tf) TC_CUDA(cudaMemcpyAsync(w.fl_TF, flags_TF, N, cudaMemcpyDeviceToDevice, c->stream));
     for (int it = 0; it <= iterations; it++) {
         int64_t r0 = T == 1 ? 0 : radii[2 * it], r1 = radii[2 * it + 1];
         bool final_pass = it == iterations;
@@ -145,9 +143,6 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
         s.resid = work_FT; s.flags = w.fl_FT; s.range_lo = range_lo; s.range_hi = range_hi;
         s.thr_mult = MAD_NORMAL * reject; s.mode = CS_BACKGROUND; s.take_abs = 0; s.medians = nullptr;
         TC_TRY(launch_chunk_select(c, s, np * nchunks, max_range));
-        // the next time-axis filter reads the flags in TF
-        bool next_tf = need_tf && radii[2 * (it + 1)] > 0;
-        if (next_tf) TC_TRY(launch_transpose<u8>(c, w.fl_FT, w.fl_TF, np, Fa, T));
     }
     // _linearly_interpolate_nans along frequency for every (plane, dump): one
     // warp per contiguous (T,F) row

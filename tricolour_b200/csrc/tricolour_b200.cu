@@ -610,7 +610,6 @@ int tc_stage_masked_filter(tc_context *c, const float *data, const uint8_t *flag
     BgWork w;
     TC_TRY(dev_bg_work_alloc(c, n, true, &w));
     TC_CUDA(cudaMemcpyAsync(w.fl_FT, s.f_FT, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    TC_CUDA(cudaMemcpyAsync(w.fl_TF, s.f_TF, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     float *o_FT, *o_TF;
     TC_TRY(tc_alloc(c, (size_t)n, &o_FT));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)n, space, &o_TF));

@@ -307,6 +307,7 @@ k_chunk_select(ChunkSelectArgs a)
     __shared__ uint32_t hist[TC_SEL_BINS];
     __shared__ uint32_t s_prefix, s_remaining, s_total, s_best;
     __shared__ double s_thr;
+    if (a.todo && !a.todo[blockIdx.x]) return;  // fallback launch: only ranges whose bracket missed
     const int64_t lo = a.range_lo[blockIdx.x], hi = a.range_hi[blockIdx.x];
     const int tid = threadIdx.x, nt = blockDim.x;
     const float sub = a.sub ? (float)a.sub[blockIdx.x] : 0.0f;
@@ -385,7 +386,8 @@ k_chunk_select(ChunkSelectArgs a)
         med = median_from_pair(lower, upper, (int)total);
     }
     if (a.medians && tid == 0) a.medians[blockIdx.x] = med;
-    if (a.mode == CS_REPORT) return;
+    if (a.medbuf && tid == 0) a.medbuf[blockIdx.x] = med;
+    if (a.mode == CS_REPORT || a.todo) return;
     if (a.mode == CS_BACKGROUND) {
         // threshold *= MAD_NORMAL * reject (float64); residual > threshold flags
         double thr = med * a.thr_mult;
@@ -798,7 +800,8 @@ k_brk_select(ChunkSelectArgs a, const BrkState *__restrict__ st, const uint32_t 
 {
     __shared__ uint32_t hist[TC_SEL_BINS];
     __shared__ uint32_t s_prefix, s_remaining, s_best;
-    const int range = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ uint32_t s_wsum[16];
+    const int range = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;  // launched with 512 threads
     const BrkState b = st[range];
     if (b.done) return;
     if (b.n_valid == 0) {
@@ -826,14 +829,32 @@ k_brk_select(ChunkSelectArgs a, const BrkState *__restrict__ st, const uint32_t 
             if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t rem = remaining, acc = 0, digit = 0;
-            for (uint32_t q = 0; q <= dmask; q++) {
-                if (rem < acc + hist[q]) { digit = q; break; }
-                acc += hist[q];
+        {
+            // parallel search of the digit: thread t owns bins [4t, 4t+4)
+            const int per = TC_SEL_BINS / 512;
+            uint32_t loc[TC_SEL_BINS / 512];
+            uint32_t sum = 0;
+            for (int q = 0; q < per; q++) { loc[q] = hist[tid * per + q]; sum += loc[q]; }
+            // inclusive scan of `sum` over the 512 threads
+            uint32_t inc = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+                if ((tid & 31) >= o) inc += v;
             }
-            s_remaining = rem - acc;
-            s_prefix = prefix | (digit << shift);
+            if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < (tid >> 5); w++) woff += s_wsum[w];
+            const uint32_t excl = woff + inc - sum;
+            if (remaining >= excl && remaining < excl + sum) {
+                uint32_t acc = excl, digit = tid * per;
+                for (int q = 0; q < per; q++) {
+                    if (remaining < acc + loc[q]) { digit = tid * per + q; break; }
+                    acc += loc[q];
+                }
+                s_remaining = remaining - acc;
+                s_prefix = prefix | (digit << shift);
+            }
         }
         __syncthreads();
         prefix = s_prefix;
@@ -896,10 +917,22 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     tc_prof_end(c);
     TC_KERNEL_CHECK();
     if (!small) {
-        // redo the (rare) ranges whose bracket missed with the sliced radix select
+        // redo the (rare) ranges whose bracket missed with the one-block radix
+        // select; blocks of all other ranges exit at once
         ChunkSelectArgs f = a;
         f.todo = todo;
-        TC_TRY(launch_chunk_select_multi(c, f, nranges, max_range, false));
+        tc_prof_begin(c, TCP_CHUNK_SELECT);
+        for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
+            unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);
+            ChunkSelectArgs b = f;
+            b.range_lo += r0; b.range_hi += r0; b.todo += r0; b.medbuf += r0;
+            if (b.sub) b.sub += r0;
+            if (b.medians) b.medians += r0;
+            TC_LAUNCH(k_chunk_select, nr, 1024, 0, c->stream, b);
+            c->launches++;
+        }
+        tc_prof_end(c);
+        TC_KERNEL_CHECK();
     }
     if (a.mode != CS_REPORT) {
         tc_prof_begin(c, TCP_CHUNK_SELECT);

@@ -206,41 +206,57 @@ struct StScanArgs {
     float scale[TC_MAX_WINDOWS];
     int mpad;                 // max padded chunk length
     double *cum;              // [nplanes][nchunks][mpad+1][ninner]
-    u8 *pn;                   // [nplanes][nchunks][mpad][ninner]
+    u8 *pn;                   // [nplanes][nchunks][mpad][ninner] pos/neg state (ping)
+    u8 *pn2;                  // same size (pong)
 };
 
-// One SumThreshold window over a padded chunk.  The prefix values that the
-// window sums need (cum[i+1-w]) are kept in a w-deep register ring when w is
-// 1, 2, 4 or 8 (every default.yaml time window and all but one frequency
-// list); other widths spill the prefix to the coalesced global scratch.
+// One SumThreshold window over a padded chunk.  The pos/neg state of the
+// previous windows is read from `pin` and the updated state written to `pout`
+// (two separate scratch planes, so that loads can run ahead of the stores; a
+// pass never reads a byte it has already rewritten).  The prefix values the
+// window sums need (cum[i+1-w]) stay in a w-deep register ring when w is 1, 2,
+// 4 or 8 (every default.yaml time window and all but one frequency list); other
+// widths spill the prefix to the coalesced global scratch.
 template <int W>
-__device__ __forceinline__ void st_window_reg(const float *d, u8 *pn, int m, int64_t es, int64_t ss,
+__device__ __forceinline__ void st_window_reg(const float *__restrict__ d, const u8 *__restrict__ pin,
+                                              u8 *__restrict__ pout, int m, int64_t es, int64_t ss,
                                               double limit, double sc, double nsc)
 {
     double h[W];
+    u8 sr[W];
 #pragma unroll
-    for (int k = 0; k < W; k++) h[k] = 0.0;
+    for (int k = 0; k < W; k++) { h[k] = 0.0; sr[k] = 0; }
     double c = 0.0;
     int lastpos = -(1 << 30), lastneg = -(1 << 30);
     for (int i0 = 0; i0 < m; i0 += 8) {
+        float xv[8];
+        u8 sv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + k;
+            xv[k] = i < m ? d[(int64_t)i * es] : 0.f;
+            sv[k] = (pin && i < m) ? pin[(int64_t)i * ss] : (u8)0;
+        }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int i = i0 + k;
             if (i < m) {
-                double x = (double)d[(int64_t)i * es];
-                const u8 st = pn[(int64_t)i * ss];
+                double x = (double)xv[k];
+                const u8 st = sv[k];
                 if ((st & 1) && x > limit) x = limit;
                 else if ((st & 2) && x < -limit) x = -limit;
                 c = c + x;
                 const int j = i + 1 - W;
-                const double cj = h[k % W];  // cum[j] (0 for j == 0)
+                const double cj = h[k % W];   // cum[j] (0 for j == 0)
+                const u8 sj = W == 1 ? st : sr[(k + 1) % W];  // state of sample j, stored W-1 steps ago
                 h[k % W] = c;
+                sr[k % W] = st;
                 if (j >= 0) {
                     const double avg = c - cj;
                     if (avg * sc > limit) lastpos = j;
                     if (avg * nsc > limit) lastneg = j;
                     const u8 add = (u8)(((j - lastpos < W) ? 1 : 0) | ((j - lastneg < W) ? 2 : 0));
-                    if (add) pn[(int64_t)j * ss] |= add;
+                    pout[(int64_t)j * ss] = (u8)(sj | add);
                 }
             }
         }
@@ -248,11 +264,13 @@ __device__ __forceinline__ void st_window_reg(const float *d, u8 *pn, int m, int
     int jt = m - W + 1; if (jt < 0) jt = 0;
     for (int j = jt; j < m; j++) {
         const u8 add = (u8)(((j - lastpos < W) ? 1 : 0) | ((j - lastneg < W) ? 2 : 0));
-        if (add) pn[(int64_t)j * ss] |= add;
+        const u8 sj = pin ? pin[(int64_t)j * ss] : (u8)0;
+        pout[(int64_t)j * ss] = (u8)(sj | add);
     }
 }
 
-__device__ __forceinline__ void st_window_mem(const float *d, u8 *pn, double *cum, int m, int w, int64_t es,
+__device__ __forceinline__ void st_window_mem(const float *__restrict__ d, const u8 *__restrict__ pin,
+                                              u8 *__restrict__ pout, double *cum, int m, int w, int64_t es,
                                               int64_t ss, double limit, double sc, double nsc)
 {
     double c = 0.0;
@@ -260,7 +278,7 @@ __device__ __forceinline__ void st_window_mem(const float *d, u8 *pn, double *cu
     int lastpos = -(1 << 30), lastneg = -(1 << 30);
     for (int i = 0; i < m; i++) {
         double x = (double)d[(int64_t)i * es];
-        const u8 st = pn[(int64_t)i * ss];
+        const u8 st = pin ? pin[(int64_t)i * ss] : (u8)0;
         if ((st & 1) && x > limit) x = limit;
         else if ((st & 2) && x < -limit) x = -limit;
         c = c + x;
@@ -271,13 +289,15 @@ __device__ __forceinline__ void st_window_mem(const float *d, u8 *pn, double *cu
             if (avg * sc > limit) lastpos = j;
             if (avg * nsc > limit) lastneg = j;
             const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-            if (add) pn[(int64_t)j * ss] |= add;
+            const u8 sj = pin ? pin[(int64_t)j * ss] : (u8)0;
+            pout[(int64_t)j * ss] = (u8)(sj | add);
         }
     }
     int jt = m - w + 1; if (jt < 0) jt = 0;
     for (int j = jt; j < m; j++) {
         const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-        if (add) pn[(int64_t)j * ss] |= add;
+        const u8 sj = pin ? pin[(int64_t)j * ss] : (u8)0;
+        pout[(int64_t)j * ss] = (u8)(sj | add);
     }
 }
 
@@ -301,25 +321,30 @@ k_st_scan(StScanArgs a)
     const float *d = a.data + plane * a.outer_stride + inner + (int64_t)p0 * a.estride;
     u8 *o = a.out + plane * a.outer_stride + inner + (int64_t)c0 * a.estride;
     int64_t sbase = ((plane * a.nchunks + chunk) * (int64_t)(a.mpad + 1)) * a.ninner + inner;
-    double *cum = a.cum + sbase;
-    u8 *pn = a.pn + ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
+    double *cum = a.cum ? a.cum + sbase : nullptr;
+    int64_t pbase = ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
+    u8 *pa = a.pn + pbase, *pb = a.pn2 + pbase;
     const int64_t es = a.estride, ss = a.ninner;
     float thr = a.thr[line * a.nchunks + chunk];
 
-    for (int i = 0; i < m; i++) pn[(int64_t)i * ss] = 0;
+    const u8 *pin = nullptr;   // no state before the first window
+    u8 *pout = pa;
     for (int wi = 0; wi < a.nwin; wi++) {
         const int w = (int)a.windows[wi];
         const double limit = (double)thr / a.tf[wi];
         const double sc = (double)a.scale[wi];
         const double nsc = (double)(-a.scale[wi]);
-        if (w == 1) st_window_reg<1>(d, pn, m, es, ss, limit, sc, nsc);
-        else if (w == 2) st_window_reg<2>(d, pn, m, es, ss, limit, sc, nsc);
-        else if (w == 4) st_window_reg<4>(d, pn, m, es, ss, limit, sc, nsc);
-        else if (w == 8) st_window_reg<8>(d, pn, m, es, ss, limit, sc, nsc);
-        else st_window_mem(d, pn, cum, m, w, es, ss, limit, sc, nsc);
+        if (w == 1) st_window_reg<1>(d, pin, pout, m, es, ss, limit, sc, nsc);
+        else if (w == 2) st_window_reg<2>(d, pin, pout, m, es, ss, limit, sc, nsc);
+        else if (w == 4) st_window_reg<4>(d, pin, pout, m, es, ss, limit, sc, nsc);
+        else if (w == 8) st_window_reg<8>(d, pin, pout, m, es, ss, limit, sc, nsc);
+        else st_window_mem(d, pin, pout, cum, m, w, es, ss, limit, sc, nsc);
+        pin = pout;
+        pout = (pout == pa) ? pb : pa;
     }
+    const u8 *pn = pin;
     int rel = c0 - p0;
-    for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = pn[(int64_t)(rel + i) * ss] ? 1 : 0;
+    for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = (pn && pn[(int64_t)(rel + i) * ss]) ? 1 : 0;
 }
 
 // ----------------------------------------------------------------------------

@@ -627,10 +627,10 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in,
 
 // ----------------------------------------------------------------------------
 // Bracket select: the exact median in two sweeps over the data instead of four.
-//   1. k_brk_sample   a stratified sample of 2048 keys per range is sorted in
+//   1. k_brk_sample   a stratified sample of 4096 keys per range is sorted in
 //                     shared memory; keys at sample ranks mid -+ delta bracket
 //                     the true median with overwhelming probability.  Ranges
-//                     of at most 2048 samples are sorted outright (exact).
+//                     of at most 4096 samples are sorted outright (exact).
 //   2. k_brk_collect  one sweep: count the keys below the bracket, copy the keys
 //                     inside it (a few percent) to a compact buffer.
 //   3. k_brk_select   radix select of rank (n/2 - below) inside the compact
@@ -639,7 +639,8 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in,
 //      sliced radix select; k_sel_update applies the thresholds.
 // The result is the same exact order statistic; only the visiting order differs.
 // ----------------------------------------------------------------------------
-#define TC_BRK_SAMPLES 2048
+#define TC_BRK_SAMPLES 4096
+#define TC_BRK_SLICE 16384   // samples per collecting block (its shared stage holds half of that)
 
 struct BrkState {
     uint32_t lo, hi;        // bracket keys (inclusive)
@@ -736,8 +737,8 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     __shared__ uint32_t s_valid, s_below, s_in, s_base;
     const int range = blockIdx.y;
     if (st[range].done) return;
-    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
-    int64_t hi = lo + TC_SEL_SLICE;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_BRK_SLICE;
+    int64_t hi = lo + TC_BRK_SLICE;
     if (hi > a.range_hi[range]) hi = a.range_hi[range];
     if (lo >= hi) return;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
@@ -893,7 +894,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     TC_TRY(tc_alloc(c, (size_t)nranges, &todo));
     if (!a.medbuf) TC_TRY(tc_alloc(c, (size_t)nranges, &a.medbuf));
     const bool small = max_range <= TC_BRK_SAMPLES;
-    const int64_t cap = small ? 1 : max_range / 8 + 4096;
+    const int64_t cap = small ? 1 : max_range / 4 + 4096;
     uint32_t *cbuf = nullptr;
     if (!small) TC_TRY(tc_alloc(c, (size_t)nranges * cap, &cbuf));
     unsigned slices = (unsigned)((max_range + TC_SEL_SLICE - 1) / TC_SEL_SLICE);
@@ -909,18 +910,40 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         TC_LAUNCH(k_brk_sample, nr, 256, 0, c->stream, b, st + r0, todo + r0);
         c->launches++;
         if (!small) {
-            TC_LAUNCH(k_brk_collect, dim3(slices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap);
+            unsigned cslices = (unsigned)((max_range + TC_BRK_SLICE - 1) / TC_BRK_SLICE);
+            TC_LAUNCH(k_brk_collect, dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap);
             TC_LAUNCH(k_brk_select, nr, 512, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap, todo + r0);
             c->launches += 2;
         }
     }
     tc_prof_end(c);
     TC_KERNEL_CHECK();
+    if (!small && getenv("TC_DEBUG_SELECT")) {
+        std::vector<unsigned> h((size_t)nranges);
+        std::vector<BrkState> hs((size_t)nranges);
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpyAsync(h.data(), todo, sizeof(unsigned) * (size_t)nranges, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hs.data(), st, sizeof(BrkState) * (size_t)nranges, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        int64_t nt = 0, nover = 0, nmiss = 0;
+        for (int64_t r = 0; r < nranges; r++)
+            if (h[r]) {
+                nt++;
+                if ((int64_t)hs[r].n_in > cap) nover++; else nmiss++;
+            }
+        fprintf(stderr, "[tc select] ranges=%lld max_range=%lld mode=%d fallback=%lld (overflow %lld, miss %lld)\n",
+                (long long)nranges, (long long)max_range, a.mode, (long long)nt, (long long)nover, (long long)nmiss);
+    }
     if (!small) {
         // redo the (rare) ranges whose bracket missed with the one-block radix
         // select; blocks of all other ranges exit at once
         ChunkSelectArgs f = a;
         f.todo = todo;
+        if (max_range > 8 * TC_SEL_SLICE) {
+            // very long ranges: one block per range would crawl, use the sliced radix select
+            TC_TRY(launch_chunk_select_multi(c, f, nranges, max_range, false));
+            goto fallback_done;
+        }
         tc_prof_begin(c, TCP_CHUNK_SELECT);
         for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
             unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);
@@ -934,6 +957,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         tc_prof_end(c);
         TC_KERNEL_CHECK();
     }
+fallback_done:
     if (a.mode != CS_REPORT) {
         tc_prof_begin(c, TCP_CHUNK_SELECT);
         for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {

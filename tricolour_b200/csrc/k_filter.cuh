@@ -54,6 +54,7 @@ struct FilterArgs {
 
 #define TC_FILT_U 8   // ticks per group: prefetch distance and output staging depth
 #define TC_FILT_LPW 4 // lines per warp
+#define TC_FILT_SKEW 2 // ticks by which pass p+1 trails pass p (2 takes shuffle+convert off the recurrence)
 
 // Warp-cooperative form.  The 32 lanes of a warp are 4 lines x 2 arrays x 4
 // passes: lane = pass*8 + array*4 + line.  Every lane runs the SAME loop body
@@ -86,7 +87,7 @@ __global__ void k_box_filter(FilterArgs a)
     float *stg = smem + (size_t)wib * (TC_FILT_WARP_FIXED + (SMEM_RING ? (size_t)L * 32 : 0));
     float *tile = stg + 64;                      // 2 x [8 ticks][2 arrays x 4 lines]
     float *ring = SMEM_RING ? (stg + TC_FILT_WARP_FIXED) : (a.gring + (size_t)gwarp * L * 32);
-    const int nticks = n + r4 + 3;
+    const int nticks = n + r4 + 3 * TC_FILT_SKEW;
     // window of local ticks in which this pass really receives a sample
     const int add_lo = pass == 3 ? r2 : 0;
     const int add_hi = pass == 0 ? n : (pass == 1 ? n + r2 : 0x7fffffff);
@@ -101,12 +102,13 @@ __global__ void k_box_filter(FilterArgs a)
         // same line in the transposed (plane, line, sample) layout
         const int64_t tbase = oline_ok ? oplane * (int64_t)n * nj + (oline - oplane * nj) * (int64_t)n : 0;
         double s = 0.0;
-        float y = 0.f;
+        float y = 0.f, yold = 0.f;    // this lane's last two outputs (the next pass reads the older one)
         float *rp = ring + lane;
         float *const rend = ring + (size_t)L * 32 + lane;
-        float ra = 0.f, rb = 0.f;     // raw words of the two in-flight input groups
-        unsigned fa = 1u, fb = 1u;
-        float wa = 0.f, wb = 0.f;
+        float ra = 0.f, rb = 0.f, rc = 0.f;   // raw words of the three in-flight input groups
+        unsigned fa = 1u, fb = 1u, fc = 1u;
+        float wa = 0.f, wb = 0.f, wc = 0.f;
+        int tb = 0;                   // input tile the current group reads
 
 // fetch this lane's sample of the group starting at tick T0 (raw words only:
 // nothing may depend on them until TC_FILT_PUBLISH)
@@ -133,39 +135,40 @@ __global__ void k_box_filter(FilterArgs a)
 // one tick of every lane's pass; FAST drops the warm-up / run-out predicates
 #define TC_FILT_TICK(K, T0, B, FAST)                                                   \
         {                                                                              \
-            const float prev_ = __shfl_up_sync(TC_FULL_MASK, y, 8);                    \
+            const float prev_ = __shfl_up_sync(TC_FULL_MASK, TC_FILT_SKEW == 2 ? yold : y, 8); \
             float u_ = prev_;                                                          \
             if (pass == 0) u_ = tile[(B) * 64 + (K) * 8 + lane];                       \
             float old_;                                                                \
             if (FAST) {                                                                \
                 old_ = *rp;                                                            \
             } else {                                                                   \
-                const int m_ = (T0) + (K) - pass;                                      \
+                const int m_ = (T0) + (K) - TC_FILT_SKEW * pass;                       \
                 u_ = (m_ >= add_lo && m_ < add_hi) ? u_ : 0.f;                         \
                 old_ = (m_ >= r2) ? *rp : 0.f;                                         \
             }                                                                          \
             *rp = u_;                                                                  \
             s += (double)u_;                                                           \
+            yold = y;                                                                  \
             y = (float)s;                                                              \
             s -= (double)old_;                                                         \
             if (pass == 3) stg[(K) * 8 + (lane - 24)] = y;                             \
             rp += 32;                                                                  \
             if (rp == rend) rp = ring + lane;                                          \
         }
-// one group: publish the group fetched last iteration, fetch the one after,
-// run 8 ticks, drain 32 outputs
+// one group: publish the group fetched two iterations ago, fetch the group
+// three ahead, run 8 ticks, drain 32 outputs
 #define TC_FILT_ITER(T0, B, RN, FN, WN, RP, FP, WP)                                    \
         {                                                                              \
             TC_FILT_PUBLISH(RP, FP, WP, (B) ^ 1)                                       \
-            TC_FILT_FETCH(RN, FN, WN, (T0) + 2 * TC_FILT_U)                            \
-            const int jout_ = (T0) + kk - 3 - r4;                                      \
+            TC_FILT_FETCH(RN, FN, WN, (T0) + 3 * TC_FILT_U)                            \
+            const int jout_ = (T0) + kk - 3 * TC_FILT_SKEW - r4;                       \
             const bool out_ok_ = jout_ >= 0 && jout_ < n && oline_ok;                  \
             const int64_t oidx_ = a.out_transposed ? tbase + (out_ok_ ? jout_ : 0)     \
                                                    : obase + (int64_t)(out_ok_ ? jout_ : 0) * nj; \
             float d2_ = 0.f;                                                           \
             if (MODE_OUT == FOUT_RESID && out_ok_) d2_ = a.data2[oidx_];               \
             __syncwarp();                                                              \
-            if ((T0) - 3 >= r2 && (T0) + TC_FILT_U <= n) {                             \
+            if ((T0) - 3 * TC_FILT_SKEW >= r2 && (T0) + TC_FILT_U <= n) {              \
                 _Pragma("unroll")                                                      \
                 for (int k_ = 0; k_ < TC_FILT_U; k_++) TC_FILT_TICK(k_, T0, B, true)   \
             } else {                                                                   \
@@ -186,14 +189,22 @@ __global__ void k_box_filter(FilterArgs a)
             }                                                                          \
         }
 
-        // prologue: group 0 goes straight into tile 0, group 1 stays in flight
+        // prologue: group 0 goes straight into tile 0, groups 1 and 2 stay in flight
         TC_FILT_FETCH(ra, fa, wa, 0)
         TC_FILT_PUBLISH(ra, fa, wa, 0)
         TC_FILT_FETCH(rb, fb, wb, TC_FILT_U)
-        for (int t0 = 0; t0 < nticks; t0 += 2 * TC_FILT_U) {
-            TC_FILT_ITER(t0, 0, ra, fa, wa, rb, fb, wb)
+        TC_FILT_FETCH(rc, fc, wc, 2 * TC_FILT_U)
+        tb = 0;
+        for (int t0 = 0; t0 < nticks; t0 += 3 * TC_FILT_U) {
+            // (publish set, fetch set) rotate b->a, c->b, a->c; the tile alternates
+            TC_FILT_ITER(t0, tb, ra, fa, wa, rb, fb, wb)
+            tb ^= 1;
             if (t0 + TC_FILT_U >= nticks) break;
-            TC_FILT_ITER(t0 + TC_FILT_U, 1, rb, fb, wb, ra, fa, wa)
+            TC_FILT_ITER(t0 + TC_FILT_U, tb, rb, fb, wb, rc, fc, wc)
+            tb ^= 1;
+            if (t0 + 2 * TC_FILT_U >= nticks) break;
+            TC_FILT_ITER(t0 + 2 * TC_FILT_U, tb, rc, fc, wc, ra, fa, wa)
+            tb ^= 1;
         }
         __syncwarp();
 #undef TC_FILT_FETCH

@@ -1,0 +1,182 @@
+# -*- coding: utf-8 -*-
+"""GPU-only tests of the pieces around the kernels: the device-resident strategy
+executor, torch-tensor (device pointer) entry, thread re-entrancy, the
+BASELINE.json configurations at reduced baseline counts, and size-independent
+properties at full block size."""
+from multiprocessing.pool import ThreadPool
+
+import numpy as np
+import pytest
+
+import oracle
+import tricolour_b200 as tb
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(nant, F):
+    ubl = common.baselines(nant)
+    ants = common.antenna_layout(nant)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    return ubl, ants, cf, cw, masks
+
+
+def test_default_strategy_matches_oracle_chain(cuda_lib):
+    """config 2 in miniature: the 12 default.yaml tasks with the reference's
+    combine rules, device resident, against the oracle run task by task"""
+    nant, T, F = 3, 64, 512
+    ubl, ants, cf, cw, masks = _setup(nant, F)
+    vis, flags = common.make_windows(ubl.shape[0], 2, T, F, seed=101, ubl=ubl)
+    strategies = common.default_strategies()
+    want = common.run_strategies(oracle, strategies, vis, flags, ubl, ants, masks, cf, cw)
+    ex = tb.StrategyExecutor(ants, ubl, cf, cw, masks, strategies)
+    got = ex.apply_strategies(flags, vis)
+    assert got.dtype == flags.dtype and got.shape == flags.shape
+    assert (got != want).mean() <= 1e-6, int((got != want).sum())
+    # the per-function numpy API chained on the host gives the same thing
+    got2 = common.run_strategies(tb, strategies, vis, flags, ubl, ants, masks, cf, cw)
+    assert np.array_equal(got, got2)
+    # autos are fully flagged, input flags survive (tasks 11 and 12)
+    assert got[ubl[:, 1] == ubl[:, 2]].all()
+    assert got[flags].all()
+
+
+def test_device_tensor_api(cuda_lib):
+    import torch
+    vis, flags = common.make_windows(2, 2, 48, 256, seed=102)
+    dv, df = torch.from_numpy(vis).cuda(), torch.from_numpy(flags).cuda()
+    kw = dict(common.DEFAULT_STRATEGY_KW["final_st_broad"])
+    out = tb.sum_threshold_flagger(dv, df, **kw)
+    assert out.is_cuda and out.dtype == torch.bool
+    assert np.array_equal(out.cpu().numpy(), tb.sum_threshold_flagger(vis, flags, **kw))
+    assert np.array_equal(tb.flag_nans_and_zeros(dv, df).cpu().numpy(), oracle.flag_nans_and_zeros(vis, flags))
+    uv = tb.uvcontsub_flagger(dv, df, major_cycles=2, sigma=15.0)
+    assert np.array_equal(uv.cpu().numpy(), tb.uvcontsub_flagger(vis, flags, major_cycles=2, sigma=15.0))
+    # inputs untouched
+    assert np.array_equal(dv.cpu().numpy(), vis, equal_nan=True) and np.array_equal(df.cpu().numpy(), flags)
+    # a non-default stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out2 = tb.sum_threshold_flagger(dv, df, **kw)
+    s.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_thread_reentrancy(cuda_lib):
+    """dask calls the functions from a ThreadPool (app.py:266-271)"""
+    blocks = [common.make_windows(1, 2, 40, 200, seed=200 + i) for i in range(6)]
+    kw = dict(outlier_nsigma=10, background_iterations=3, num_major_iterations=2)
+    serial = [tb.sum_threshold_flagger(v, f, **kw) for v, f in blocks]
+    with ThreadPool(4) as pool:
+        par = pool.starmap(lambda v, f: tb.sum_threshold_flagger(v, f, **kw), blocks)
+    for a, b in zip(serial, par):
+        assert np.array_equal(a, b)
+    assert np.array_equal(serial[0], oracle.sum_threshold_flagger(*blocks[0], **kw))
+
+
+def test_config3_polarised_wideband(cuda_lib):
+    """config 3 in miniature: rows (T*nbl, 32768 chan, 4 corr) -> Q,U,V polarised
+    intensity -> windows (nbl, 1, T, 32768) -> sum_threshold"""
+    nant, T, F = 2, 16, 32768
+    ubl = common.baselines(nant)
+    nbl = ubl.shape[0]
+    rs = np.random.RandomState(5)
+    a1 = np.tile(ubl[:, 1], T).astype(np.int32)
+    a2 = np.tile(ubl[:, 2], T).astype(np.int32)
+    tinv = np.repeat(np.arange(T), nbl)
+    rows = (rs.standard_normal((T * nbl, F, 4)) + 1j * rs.standard_normal((T * nbl, F, 4))).astype(np.complex64)
+    rows[:, 1000:1003] += 40
+    smap = tb.stokes_corr_map([9, 10, 11, 12])
+    pol = tuple(v for k, v in smap.items() if k != 'I')
+    pi = tb.polarised_intensity(rows, pol)
+    np.testing.assert_allclose(pi.real, oracle.polarised_intensity(rows, pol).real, rtol=1.2e-7)
+    flags = np.zeros(pi.shape, bool)
+    vw, fw = tb.pack_data(tinv, ubl, a1, a2, pi, flags, T)
+    assert vw.shape == (nbl, 1, T, F)
+    kw = dict(common.DEFAULT_STRATEGY_KW["final_st_very_broad"])
+    got = tb.sum_threshold_flagger(vw, fw, **kw)
+    want = oracle.sum_threshold_flagger(vw, fw, nthreads=4, **kw)
+    assert np.array_equal(got, want)
+    assert got[:, :, :, 1000:1003].mean() > 0.9
+
+
+def test_config4_uvcontsub_then_sumthreshold(cuda_lib):
+    """config 4 in miniature: default.yaml tasks 4..7 on 1024 dumps, cross baselines"""
+    nant, T, F = 3, 1024, 256
+    ubl = common.baselines(nant, autos=False)
+    ants = common.antenna_layout(nant)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    vis, flags = common.make_windows(ubl.shape[0], 2, T, F, seed=104, ubl=ubl)
+    strategies = common.default_strategies()[3:7]
+    want = common.run_strategies(oracle, strategies, vis, flags, ubl, ants, masks, cf, cw)
+    got = tb.StrategyExecutor(ants, ubl, cf, cw, masks, strategies).apply_strategies(flags, vis)
+    assert (got != want).mean() <= 1e-6
+
+
+def test_config5_rows_to_rows(cuda_lib):
+    """config 5 in miniature: MS row order -> pack -> strategy -> unpack (+corr
+    equalisation) -> window statistics, baselines split over two 'ranks'"""
+    nant, T, F, ncorr = 4, 32, 128, 4
+    ubl, ants, cf, cw, masks = _setup(nant, F)
+    nbl = ubl.shape[0]
+    vis_w, flag_w = common.make_windows(nbl, ncorr, T, F, seed=105, ubl=ubl)
+    vis_w = np.nan_to_num(vis_w, nan=0.0)
+    # row order: time-major, one row per (t, baseline)
+    a1 = np.tile(ubl[:, 1], T).astype(np.int32)
+    a2 = np.tile(ubl[:, 2], T).astype(np.int32)
+    tinv = np.repeat(np.arange(T), nbl)
+    rows = np.ascontiguousarray(vis_w.transpose(2, 0, 3, 1).reshape(T * nbl, F, ncorr))
+    rflags = np.ascontiguousarray(flag_w.transpose(2, 0, 3, 1).reshape(T * nbl, F, ncorr))
+    strategies = common.default_strategies()[:3] + common.default_strategies()[10:]
+    names = ["m%03d" % i for i in range(nant)]
+    outs, stats = [], []
+    for lo, hi in ((0, nbl // 2), (nbl // 2, nbl)):       # two baseline shards
+        sub = ubl[lo:hi]
+        vw, fw = tb.pack_data(tinv, np.concatenate([np.arange(hi - lo, dtype=np.int32)[:, None], sub[:, 1:]], 1),
+                              a1, a2, rows, rflags, T)
+        assert np.array_equal(vw, vis_w[lo:hi]) and np.array_equal(fw, flag_w[lo:hi])
+        su = sub.copy()
+        su[:, 0] -= su[0, 0]
+        fl = tb.StrategyExecutor(ants, su, cf, cw, masks, strategies).apply_strategies(fw, vw)
+        want = common.run_strategies(oracle, strategies, vw, fw, su, ants, masks, cf, cw)
+        assert np.array_equal(fl, want)
+        outs.append((su, fl))
+        stats.append(tb.window_stats(fl, sub, cf, names, 0, "f", 0))
+    total = tb.combine_window_stats(stats)
+    full = np.concatenate([o[1] for o in outs])
+    assert int(total._counts_per_field["f"]) == int(full.sum())
+    # unpack every shard back to row order and OR them (each row belongs to one shard)
+    unp = np.zeros(rflags.shape, bool)
+    for su, fl in outs:
+        sel = np.concatenate([np.arange(su.shape[0], dtype=np.int32)[:, None], su[:, 1:]], 1)
+        unp |= tb.packing.unpack_flags_equalised(a1, a2, tinv, sel, fl)
+    expect = full.transpose(2, 0, 3, 1).reshape(T * nbl, F, ncorr)
+    expect = np.broadcast_to(expect.any(axis=2, keepdims=True), expect.shape)
+    assert np.array_equal(unp, expect)
+
+
+def test_full_block_properties(cuda_lib):
+    """one dask block of config 2 at full size (8 baselines to keep it short):
+    no oracle, size-independent properties only"""
+    nbl, ncorr, T, F = 8, 4, 512, 4096
+    ubl = common.baselines(64)[:nbl]
+    vis, flags = common.make_windows(nbl, ncorr, T, F, seed=106, ubl=ubl)
+    nz = tb.flag_nans_and_zeros(vis, flags)
+    assert np.array_equal(nz, flags | (vis == 0) | np.isnan(vis))
+    assert np.array_equal(tb.flag_nans_and_zeros(vis, nz), nz)            # idempotent
+    kw = dict(common.DEFAULT_STRATEGY_KW["final_st_broad"])
+    a = tb.sum_threshold_flagger(vis, nz, **kw)
+    b = tb.sum_threshold_flagger(vis, nz, **kw)
+    assert np.array_equal(a, b)                                            # deterministic
+    # planes are independent: a sub-block gives the same flags as inside the batch
+    c = tb.sum_threshold_flagger(vis[2:4], nz[2:4], **kw)
+    assert np.array_equal(a[2:4], c)
+    assert a[np.isnan(vis)].all()                                          # isnan OR (flagging.py:776-781)
+    # one plane against the oracle at full size
+    d = oracle.sum_threshold_flagger(vis[5:6, 1:2], nz[5:6, 1:2], **kw)
+    assert np.array_equal(a[5:6, 1:2], d)
+    st = tb.window_stats(a, ubl, common.channels(F)[0], ["m%03d" % i for i in range(64)], 0, "f", 0)
+    assert int(st._counts_per_field["f"]) == int(a.sum())

@@ -577,3 +577,24 @@ def test_golden_uvcontsub(backend):
     assert (got != g["cycles7"][:vis.shape[0], :vis.shape[1]]).mean() <= 1e-4
     got = tb.uvcontsub_flagger(vis, flags, major_cycles=3, or_original_from_cycle=0, taylor_degrees=25, sigma=13.0)
     assert (got != g["cycles3_or0"][:vis.shape[0], :vis.shape[1]]).mean() <= 1e-4
+
+
+def test_strategy_chain(backend):
+    """strat_executor.py combine rules with the per-function numpy API"""
+    nant = 2
+    ubl = common.baselines(nant)
+    ants = common.antenna_layout(nant)
+    T, F = (48, 256) if big(backend) else (16, 64)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    vis, flags = common.make_windows(ubl.shape[0], 2, T, F, seed=31, ubl=ubl)
+    strategies = common.default_strategies()
+    if not big(backend):
+        for s in strategies:           # keep the emulated run short
+            if s["task"] == "sum_threshold":
+                s["kwargs"].update(num_major_iterations=1, background_iterations=2)
+            if s["task"] == "uvcontsub_flagger":
+                s["kwargs"].update(major_cycles=2)
+    got = common.run_strategies(tb, strategies, vis, flags, ubl, ants, masks, cf, cw)
+    want = common.run_strategies(oracle, strategies, vis, flags, ubl, ants, masks, cf, cw)
+    assert (got != want).mean() <= 1e-6

@@ -267,9 +267,18 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
     const size_t per_warp = ((size_t)2 * a.r * 32 + TC_FILT_WARP_FIXED) * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;
     if (per_warp <= smem_cap) {
-        // 4 warps (16 lines) per block unless the delay lines are too deep
-        int wpb = (int)(smem_cap / per_warp);
-        if (wpb > 4) wpb = 4;
+        // warps per block: whatever packs the most warps into an SM's shared
+        // memory (1 KB is reserved per block), at least 2 blocks per SM in flight
+        int wpb = 1, best = 0;
+        for (int w = 1; w <= 8; w++) {
+            size_t need = per_warp * w + 1024;
+            if (need > (size_t)c->smem_optin) break;
+            int blocks = (int)((size_t)(c->smem_optin + 1024) / need);
+            if (blocks > 32) blocks = 32;
+            int warps = blocks * w;
+            if (warps > 32) warps = 32;      // register file: 64 regs x 32 warps
+            if (warps > best || (warps == best && w <= 4)) { best = warps; wpb = w; }
+        }
         while (wpb > 1 && (ngroups + wpb - 1) / wpb < 2 * (int64_t)c->sm_count) wpb--;
         size_t smem = per_warp * wpb;
         unsigned grid = (unsigned)((ngroups + wpb - 1) / wpb);

@@ -255,7 +255,7 @@ def ours(args):
     vis, flags = make_block_torch(B, NCORR, T, F, bl0, ubl, dev, 20261019 + rank)
     ex = tb.StrategyExecutor(ants, my_ubl, cf, cw, masks, strategies)
     nvis = B * NCORR * T * F
-    ctx = _cabi.get_context(local, torch.cuda.current_stream(dev).cuda_stream)
+    ctx = _cabi.get_context(local, _cabi.torch_stream_handle(local))
 
     def barrier():
         if world > 1:

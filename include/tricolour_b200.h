@@ -47,8 +47,9 @@ typedef struct tc_context tc_context;
 /* ---- runtime ---------------------------------------------------------- */
 const char *tc_last_error(void);
 int tc_device_count(void);
-/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
- * to let the context create its own non-blocking stream. */
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream; pass
+ * cudaStreamLegacy, (void *)1, for the default stream), or NULL to let the
+ * context create its own non-blocking stream. */
 int tc_context_create(int device, void *stream, tc_context **out);
 void tc_context_destroy(tc_context *ctx);
 int tc_synchronize(tc_context *ctx);

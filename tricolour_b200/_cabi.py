@@ -243,6 +243,18 @@ def ptr(a):
     return _vp(a.ctypes.data)
 
 
+CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the handle that names torch's default stream
+
+
+def torch_stream_handle(device_index):
+    """cudaStream_t of torch's current stream on ``device_index``.  torch reports
+    the default stream as 0; the library treats NULL as "create your own stream",
+    so the legacy default stream is passed by its explicit handle instead."""
+    import torch
+    h = int(torch.cuda.current_stream(device_index).cuda_stream)
+    return h if h else CUDA_STREAM_LEGACY
+
+
 def context_for(*arrays):
     """Host arrays -> thread default context; device tensors -> a context bound
     to torch's current stream on the tensors' device."""
@@ -250,8 +262,7 @@ def context_for(*arrays):
         if is_device_array(a):
             import torch
             dev = a.device.index if a.device.index is not None else torch.cuda.current_device()
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            return get_context(dev, stream), DEVICE
+            return get_context(dev, torch_stream_handle(dev)), DEVICE
     return get_context(), HOST
 
 

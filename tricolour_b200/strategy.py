@@ -31,7 +31,7 @@ def _flags_or(a, b):
     bu8 = b.view(torch.uint8) if b.dtype == torch.bool else b
     out = torch.empty_like(au8)
     dev = a.device.index if a.device.index is not None else torch.cuda.current_device()
-    ctx = _cabi.get_context(dev, torch.cuda.current_stream(dev).cuda_stream)
+    ctx = _cabi.get_context(dev, _cabi.torch_stream_handle(dev))
     check(_cabi.load().tc_flags_or(ctx.handle, ptr(au8.contiguous()), ptr(bu8.contiguous()),
                                    ptr(out), int(out.numel()), _cabi.DEVICE))
     return out.view(torch.bool) if a.dtype == torch.bool else out

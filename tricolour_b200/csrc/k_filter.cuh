@@ -94,8 +94,7 @@ __global__ void k_box_filter(FilterArgs a)
     // load / drain role of this lane: tick kk of a group, line qq of the warp
     const int kk = lane >> 2, qq = lane & 3;
 
-    const int64_t ngroups_pad = (ngroups + nwb - 1) / nwb * nwb;
-    for (int64_t grp = gwarp; grp < ngroups_pad; grp += nwarps) {
+    for (int64_t grp = gwarp; grp < ngroups; grp += nwarps) {
         const int64_t oline = grp * TC_FILT_LPW + qq;
         const bool oline_ok = oline < a.nlines;
         const int64_t oplane = oline_ok ? oline / nj : 0;
@@ -168,7 +167,7 @@ __global__ void k_box_filter(FilterArgs a)
                                                    : obase + (int64_t)(out_ok_ ? jout_ : 0) * nj; \
             float d2_ = 0.f;                                                           \
             if (MODE_OUT == FOUT_RESID && out_ok_) d2_ = a.data2[oidx_];               \
-            __syncthreads();                                                           \
+            __syncwarp();                                                              \
             if ((T0) - 3 * TC_FILT_SKEW >= r2 && (T0) + TC_FILT_U <= n) {              \
                 _Pragma("unroll")                                                      \
                 for (int k_ = 0; k_ < TC_FILT_U; k_++) TC_FILT_TICK(k_, T0, B, true)   \
@@ -268,13 +267,18 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
     const size_t per_warp = ((size_t)2 * a.r * 32 + TC_FILT_WARP_FIXED) * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;
     if (per_warp <= smem_cap) {
-        // Warps of a block walk neighbouring lines in step (one barrier per
-        // group), so a block reads wpb*16 contiguous bytes of every row: use big
-        // blocks (long DRAM bursts), as many warps as shared memory and the
-        // register file (64 regs x 1024 threads) allow, but keep >= 2 blocks per SM
-        int wpb = (int)((size_t)c->smem_optin / per_warp);
-        if (wpb > 16) wpb = 16;
-        if (wpb < 1) wpb = 1;
+        // warps per block: whatever packs the most warps into an SM's shared
+        // memory (1 KB is reserved per block), at least 2 blocks per SM in flight
+        int wpb = 1, best = 0;
+        for (int w = 1; w <= 8; w++) {
+            size_t need = per_warp * w + 1024;
+            if (need > (size_t)c->smem_optin) break;
+            int blocks = (int)((size_t)(c->smem_optin + 1024) / need);
+            if (blocks > 32) blocks = 32;
+            int warps = blocks * w;
+            if (warps > 32) warps = 32;      // register file: 64 regs x 32 warps
+            if (warps > best || (warps == best && w <= 4)) { best = warps; wpb = w; }
+        }
         while (wpb > 1 && (ngroups + wpb - 1) / wpb < 2 * (int64_t)c->sm_count) wpb--;
         size_t smem = per_warp * wpb;
         unsigned grid = (unsigned)((ngroups + wpb - 1) / wpb);

@@ -567,18 +567,46 @@ k_sel_update(ChunkSelectArgs a)
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
     int64_t hi = lo + TC_SEL_SLICE;
     if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    if (lo >= hi) return;
     const double med = a.medbuf[range];
+    double thr;
+    bool replace = false;
     if (a.mode == CS_BACKGROUND) {
-        double thr = med * a.thr_mult;
-        if (thr != thr) return;
-        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-            if ((double)a.resid[i] > thr) a.flags[i] = 1;
+        // threshold *= MAD_NORMAL * reject (float64); residual > threshold flags
+        thr = med * a.thr_mult;
+        if (thr != thr) return;  // NaN threshold never flags
     } else if (a.mode == CS_UVCONTSUB) {
-        if (a.uv_unflagged[range] == 0) return;
-        float thr = a.uv_sigma * (float)med;
+        if (a.uv_unflagged[range] == 0) return;     // fully flagged plane: untouched
+        thr = (double)(a.uv_sigma * (float)med);    // float32 product (NEP 50); NaN never flags
+        replace = a.uv_replace != 0;
+    } else {
+        return;
+    }
+    const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
+    if (vec) {
+        const int64_t n4 = (hi - lo) >> 2;
+        for (int64_t q = threadIdx.x; q < n4; q += blockDim.x) {
+            const int64_t i = lo + q * 4;
+            const float4 x = *reinterpret_cast<const float4 *>(a.resid + i);
+            uint32_t nf = ((double)x.x > thr ? 1u : 0u) | ((double)x.y > thr ? 0x100u : 0u) |
+                          ((double)x.z > thr ? 0x10000u : 0u) | ((double)x.w > thr ? 0x1000000u : 0u);
+            uint32_t *fp = reinterpret_cast<uint32_t *>(a.flags + i);
+            if (replace) *fp = nf;
+            else if (nf) {
+                uint32_t old = *fp;
+                // keep bytes 0/1: set byte to 1 where newly flagged
+                *fp = old | nf;
+            }
+        }
+        for (int64_t i = lo + n4 * 4 + threadIdx.x; i < hi; i += blockDim.x) {
+            bool nf = (double)a.resid[i] > thr;
+            if (replace) a.flags[i] = nf ? 1 : 0;
+            else if (nf) a.flags[i] = 1;
+        }
+    } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            bool nf = a.resid[i] > thr;
-            if (a.uv_replace) a.flags[i] = nf ? 1 : 0;
+            bool nf = (double)a.resid[i] > thr;
+            if (replace) a.flags[i] = nf ? 1 : 0;
             else if (nf) a.flags[i] = 1;
         }
     }
@@ -748,29 +776,59 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     if (tid == 0) { s_valid = 0; s_below = 0; s_in = 0; }
     __syncthreads();
     uint32_t nvalid = 0, nbelow = 0;
-    for (int64_t i0 = lo; i0 < hi; i0 += nt) {
-        const int64_t i = i0 + tid;
-        bool in = false;
-        uint32_t k = 0;
-        if (i < hi && !a.flags[i]) {
-            float x = cs_value(a, i, sub);
-            if (!(a.skip_nan && x != x)) {
-                k = f2key(x);
-                nvalid++;
-                if (k < klo) nbelow++;
-                else if (k <= khi) in = true;
+    // four samples per thread and iteration: one 4-byte flag word and one 16-byte
+    // sample vector (the slice start is 4-aligned whenever the range start is)
+    const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
+    const int64_t step = vec ? (int64_t)nt * 4 : nt;
+    for (int64_t i0 = lo; i0 < hi; i0 += step) {
+        uint32_t k4[4];
+        bool in4[4] = {false, false, false, false};
+        const int64_t ib = vec ? i0 + (int64_t)tid * 4 : i0 + tid;
+        const int cntv = vec ? 4 : 1;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t fw = 0x01010101u;
+        if (vec && ib + 3 < hi) {
+            fw = *reinterpret_cast<const uint32_t *>(a.flags + ib);
+            const float4 t4 = *reinterpret_cast<const float4 *>(a.resid + ib);
+            xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
+        } else {
+            fw = 0;
+            for (int q = 0; q < cntv; q++) {
+                const int64_t i = ib + q;
+                if (i < hi) { fw |= (uint32_t)(a.flags[i] ? 1u : 0u) << (8 * q); xv[q] = a.resid[i]; }
+                else fw |= 1u << (8 * q);
             }
         }
-        const unsigned m = __ballot_sync(TC_FULL_MASK, in);
-        if (m) {
-            uint32_t base = 0;
-            const int leader = __ffs((int)m) - 1;
-            if (lane == leader) base = atomicAdd(&s_in, (uint32_t)__popc(m));
-            base = __shfl_sync(TC_FULL_MASK, base, leader);
-            if (in) {
-                uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if (slot < TC_BRK_STAGE) stage[slot] = k;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            k4[q] = 0;
+            if (q < cntv && !((fw >> (8 * q)) & 0xffu)) {
+                float x = xv[q];
+                if (a.take_abs) x = fabsf(x - sub);
+                if (!(a.skip_nan && x != x)) {
+                    const uint32_t k = f2key(x);
+                    nvalid++;
+                    if (k < klo) nbelow++;
+                    else if (k <= khi) { in4[q] = true; k4[q] = k; c++; }
+                }
             }
+        }
+        // warp-level compaction: exclusive scan of the per-thread counts, one shared atomic per warp
+        int inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int total = __shfl_sync(TC_FULL_MASK, inc, 31);
+        if (total) {
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&s_in, (uint32_t)total);
+            base = __shfl_sync(TC_FULL_MASK, base, 31);
+            uint32_t slot = base + (uint32_t)(inc - c);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (in4[q]) { if (slot < TC_BRK_STAGE) stage[slot] = k4[q]; slot++; }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

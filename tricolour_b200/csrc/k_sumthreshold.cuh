@@ -208,6 +208,7 @@ struct StScanArgs {
     double *cum;              // [nplanes][nchunks][mpad+1][ninner]
     u8 *pn;                   // [nplanes][nchunks][mpad][ninner] pos/neg state (ping)
     u8 *pn2;                  // same size (pong)
+    int fused1248;            // windows are exactly [1, 2, 4, 8]: single-sweep kernel, no scratch
 };
 
 // One SumThreshold window over a padded chunk.  The pos/neg state of the
@@ -301,6 +302,101 @@ __device__ __forceinline__ void st_window_mem(const float *__restrict__ d, const
     }
 }
 
+// All four windows of the default lists [1, 2, 4, 8] in ONE sweep.  Window k
+// only needs the flags of window k-1 at the sample it is processing, and those
+// are final W(k-1)-1 samples after window k-1 passed it, so the windows can
+// follow each other at fixed lags (0, 0, 1, 4 samples): the line is read once,
+// the pos/neg state lives in small register rings and never touches memory,
+// and the four float64 prefix chains give the scheduler independent work.
+// Per window the arithmetic is exactly st_window_reg's (sequential prefix,
+// prefix differences, smear), so the flags are identical.
+struct StW {
+    double c;
+    int lastpos, lastneg;
+};
+
+template <int W>
+__device__ __forceinline__ u8 st_step(StW &w, double *h, int slot, bool have, float xf, u8 st, int i,
+                                      double limit, double sc, double nsc)
+{
+    // processes sample i (if `have`), evaluates the window starting at j = i+1-W and
+    // returns the pos/neg bits that window coverage adds to sample j
+    const int j = i + 1 - W;
+    if (have) {
+        double x = (double)xf;
+        if ((st & 1) && x > limit) x = limit;
+        else if ((st & 2) && x < -limit) x = -limit;
+        w.c = w.c + x;
+        const double cj = h[slot];
+        h[slot] = w.c;
+        if (j >= 0) {
+            const double avg = w.c - cj;
+            if (avg * sc > limit) w.lastpos = j;
+            if (avg * nsc > limit) w.lastneg = j;
+        }
+    }
+    return (u8)(((j - w.lastpos < W) ? 1 : 0) | ((j - w.lastneg < W) ? 2 : 0));
+}
+
+__device__ __forceinline__ void st_fused_1248(const float *__restrict__ d, u8 *__restrict__ out, int m, int rel,
+                                              int nout, int64_t es, float thr, const double *tf,
+                                              const float *scale)
+{
+    const double l0 = (double)thr / tf[0], l1 = (double)thr / tf[1], l2 = (double)thr / tf[2], l3 = (double)thr / tf[3];
+    const double s0 = (double)scale[0], s1 = (double)scale[1], s2 = (double)scale[2], s3 = (double)scale[3];
+    const double n0 = (double)(-scale[0]), n1 = (double)(-scale[1]), n2 = (double)(-scale[2]), n3 = (double)(-scale[3]);
+    StW w0 = {0.0, -(1 << 30), -(1 << 30)}, w1 = w0, w2 = w0, w3 = w0;
+    double h0[1] = {0.0}, h1[2] = {0.0, 0.0}, h2[4] = {0.0, 0.0, 0.0, 0.0}, h3[8];
+    float xr[8];      // x[s - q] lives in xr[(s - q) & 7]
+    u8 p0prev = 0;    // pn_0(s-1)
+    u8 p1r[4];        // pn_1(j) in p1r[j & 3]
+    u8 p2r[8];        // pn_2(j) in p2r[j & 7]
+#pragma unroll
+    for (int k = 0; k < 8; k++) { h3[k] = 0.0; xr[k] = 0.f; p2r[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) p1r[k] = 0;
+    // window positions at step s: i0 = i1 = s, i2 = s - 1, i3 = s - 4; the last
+    // sample (m-1) leaves window 3 at step m - 1 + 7 + 4
+    for (int s0i = 0; s0i < m + 11; s0i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int s = s0i + k;
+            const float xs = s < m ? d[(int64_t)s * es] : 0.f;
+            xr[k] = xs;                                            // (s & 7) == k
+            // window 0 (W=1) at sample s, finalises pn_0(s)
+            u8 p0 = 0;
+            if (s < m) p0 = st_step<1>(w0, h0, 0, true, xs, 0, s, l0, s0, n0);
+            // window 1 (W=2) at sample s with pn_0(s), finalises pn_1(s-1)
+            {
+                const u8 add = st_step<2>(w1, h1, k & 1, s < m, xs, p0, s, l1, s1, n1);
+                const int j = s - 1;
+                if (j >= 0 && j < m) p1r[(k + 3) & 3] = (u8)(p0prev | add);
+            }
+            p0prev = p0;
+            // window 2 (W=4) at sample s-1 with pn_1(s-1), finalises pn_2(s-4)
+            {
+                const int i = s - 1;
+                const bool have = i >= 0 && i < m;
+                const u8 add = st_step<4>(w2, h2, (k + 3) & 3, have, xr[(k + 7) & 7], p1r[(k + 3) & 3], i, l2, s2, n2);
+                const int j = i - 3;
+                if (j >= 0 && j < m) p2r[(k + 4) & 7] = (u8)(p1r[k & 3] | add);   // (j & 3) == (k & 3), (j & 7) == ((k+4) & 7)
+            }
+            // window 3 (W=8) at sample s-4 with pn_2(s-4), finalises pn_3(s-11)
+            {
+                const int i = s - 4;
+                const bool have = i >= 0 && i < m;
+                const u8 add = st_step<8>(w3, h3, (k + 4) & 7, have, xr[(k + 4) & 7], p2r[(k + 4) & 7], i, l3, s3, n3);
+                const int j = i - 7;
+                if (j >= 0 && j < m) {
+                    const u8 fin = (u8)(p2r[(k + 5) & 7] | add);               // (j & 7) == ((k + 5) & 7)
+                    const int o = j - rel;
+                    if (o >= 0 && o < nout) out[(int64_t)o * es] = fin ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_st_scan(StScanArgs a)
 {
@@ -323,10 +419,14 @@ k_st_scan(StScanArgs a)
     int64_t sbase = ((plane * a.nchunks + chunk) * (int64_t)(a.mpad + 1)) * a.ninner + inner;
     double *cum = a.cum ? a.cum + sbase : nullptr;
     int64_t pbase = ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
-    u8 *pa = a.pn + pbase, *pb = a.pn2 + pbase;
+    u8 *pa = a.pn ? a.pn + pbase : nullptr, *pb = a.pn2 ? a.pn2 + pbase : nullptr;
     const int64_t es = a.estride, ss = a.ninner;
     float thr = a.thr[line * a.nchunks + chunk];
 
+    if (a.fused1248) {
+        st_fused_1248(d, o, m, c0 - p0, c1 - c0, es, thr, a.tf, a.scale);
+        return;
+    }
     const u8 *pin = nullptr;   // no state before the first window
     u8 *pout = pa;
     for (int wi = 0; wi < a.nwin; wi++) {

@@ -222,13 +222,18 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     s.outer_stride = (int64_t)T * Fa; s.estride = ninner; s.n = n; s.nchunks = nchunks;
     s.chunk_ends = d_ce; s.nwin = nwin; s.maxw = (int)maxw; s.mpad = mpad;
     for (int k = 0; k < nwin; k++) { s.windows[k] = windows[k]; s.tf[k] = tf[k]; s.scale[k] = scale[k]; }
+    s.fused1248 = (nwin == 4 && windows[0] == 1 && windows[1] == 2 && windows[2] == 4 && windows[3] == 8 &&
+                   !getenv("TC_ST_UNFUSED")) ? 1 : 0;
     bool need_cum = false;
     for (int k = 0; k < nwin; k++)
         if (windows[k] != 1 && windows[k] != 2 && windows[k] != 4 && windows[k] != 8) need_cum = true;
     s.cum = nullptr;
     if (need_cum) TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad + 1) * ninner, &s.cum));
-    TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn));
-    TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn2));
+    s.pn = s.pn2 = nullptr;
+    if (!s.fused1248) {
+        TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn));
+        TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn2));
+    }
     tc_prof_begin(c, TCP_ST_SCAN);
     TC_LAUNCH_NOSYNC(k_st_scan, tc_blocks_for(nlines * nchunks, 128), 128, 0, c->stream, s);
     tc_prof_end(c);

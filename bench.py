@@ -56,6 +56,18 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu
+    --set full capture (profiles/rNN_traffic.json, written by profiles/summarize.py)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_per_launch"), os.path.basename(files[-1])
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -328,9 +340,13 @@ def ours(args):
         total_prof = sum(v[0] for v in prof.values())
         per_launch_ms = fam_ms / max(fam_n, 1)
         achieved = nvis * BYTES_PER_VIS / (per_launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic()
+        if traffic is not None and B != 16:
+            traffic = traffic * B / 16.0     # the capture was taken on a 16-baseline block
         roofline = {
             "bound": "hbm", "kernel": fam[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": nvis * BYTES_PER_VIS, "peak_source": peak_src,
             "launches_per_step": fam_n / args.steps, "avg_launch_ms": per_launch_ms,
             "share_of_step": fam_ms / max(total_prof, 1e-9),
             "strategy": {"achieved": value / world * BYTES_PER_VIS, "frac": value / world * BYTES_PER_VIS / peak,

@@ -87,20 +87,31 @@ k_line_median(LineMedianArgs a)
     uint32_t key[VPL];
     uint32_t valid = 0;
     int cnt = 0;
+    // all loads first (independent of each other), then the keys
+    float xraw[VPL];
+    u8 fraw[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; k++) {
-        int i = lane + 32 * k;
-        key[k] = 0;
+        const int i = lane + 32 * k;
+        xraw[k] = 0.f;
+        fraw[k] = 1;
         if (i < n) {
-            int64_t idx = base + (int64_t)i * a.elem_stride;
-            bool fl = (a.flags && a.flags[idx]) || (a.flags2 && a.flags2[idx]);
-            if (!fl) {
-                float x = a.data[idx];
-                if (a.use_abs) x = fabsf(x);
-                key[k] = f2key(x);
-                valid |= 1u << k;
-                cnt++;
-            }
+            const int64_t idx = base + (int64_t)i * a.elem_stride;
+            xraw[k] = a.data[idx];
+            u8 f = a.flags ? a.flags[idx] : (u8)0;
+            if (a.flags2) f |= a.flags2[idx];
+            fraw[k] = f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; k++) {
+        key[k] = 0;
+        if (!fraw[k]) {
+            float x = xraw[k];
+            if (a.use_abs) x = fabsf(x);
+            key[k] = f2key(x);
+            valid |= 1u << k;
+            cnt++;
         }
     }
     int total = warp_sum_i(cnt);

@@ -262,6 +262,36 @@ def test_masked_gaussian_filter(backend):
         G.masked_gaussian_filter(d, fl[:1], np.array(sig), o)
 
 
+def _sigma_for_radius(r):
+    """a sigma that the reference turns into box radius r (flagging.py:451)"""
+    return float(np.sqrt(((2 * r + 1) ** 2 - 1) / 3.0)) + 1e-6 if r > 0 else 0.0
+
+
+def test_masked_gaussian_filter_radii(backend):
+    """every delay-line phase of the lean filter kernels (radius mod 4, ring
+    wrap, lines not a multiple of 8, samples not a multiple of 8)"""
+    rs = np.random.RandomState(66)
+    radii = [(4, 5), (6, 7), (5, 4), (7, 6), (8, 9), (10, 11), (13, 3), (3, 12), (9, 0), (0, 14), (17, 2)]
+    if big(backend):
+        radii += [(r, r + 1) for r in range(15, 40, 3)] + [(54, 43), (28, 277), (5, 110), (127, 16), (128, 8), (130, 131)]
+    for i, (r0, r1) in enumerate(radii):
+        if big(backend):
+            shape = [(68, 92), (128, 200), (30, 301), (252, 64), (1, 400)][i % 5]
+        else:
+            shape = [(16, 24), (12, 40), (24, 20), (13, 21), (1, 36)][i % 5]
+        sig = np.array((_sigma_for_radius(r0), _sigma_for_radius(r1)))
+        d = (rs.uniform(size=shape) * 10 ** rs.uniform(-2, 2, shape)).astype(np.float32)
+        d[rs.uniform(size=shape) < 0.01] = 0
+        d[rs.uniform(size=shape) < 0.01] *= -1
+        fl = rs.uniform(size=shape) < 0.3
+        fl[shape[0] // 4:shape[0] // 2, 2:shape[1] // 2] = True
+        o = np.zeros_like(d)
+        G.masked_gaussian_filter(d, fl, sig, o)
+        o2 = np.zeros_like(d)
+        oracle.masked_gaussian_filter(d, fl, sig, o2)
+        assert_same(o, o2, "masked filter radii (%d, %d) shape %s" % (r0, r1, shape))
+
+
 def test_get_background2d(backend):
     rs = np.random.RandomState(7)
     cases = [((95, 86), 1, (10., 10.), [0, 86]), ((45, 86), 3, (2.5, 2.5), [0, 40, 86]),

@@ -12,6 +12,7 @@
 #pragma once
 #include "k_elementwise.cuh"
 #include "k_filter.cuh"
+#include "k_filter2.cuh"
 #include "k_select.cuh"
 #include "k_sumthreshold.cuh"
 
@@ -68,7 +69,11 @@ k_abs_sub(const float *a, const float *b, float *out, int64_t n)
 }
 
 // one masked_gaussian_filter (flagging.py:469-513) from (data, work flags) to
-// out_FT; resid != 0 stores |data - background| instead (flagging.py:561-566)
+// out_FT; resid != 0 stores |data - background| instead (flagging.py:561-566).
+// The lean kernels (k_filter2.cuh) want their input line-contiguous: the time
+// axis reads the (F,T) copies, the frequency axis the (T,F) ones; whichever
+// kernel runs first writes the intermediate (value, weight) pair in the layout
+// the second one reads.
 static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const float *data_TF,
                              const float *data_FT, BgWork &w, int64_t r0, int64_t r1, int resid,
                              float *out_FT)
@@ -76,25 +81,34 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     int64_t N = np * (int64_t)T * Fa;
     FilterArgs a;
     memset(&a, 0, sizeof(a));
+    FilterArgs probe;
+    memset(&probe, 0, sizeof(probe));
+    probe.n = T; probe.r = (int)r0;
+    const bool lean0 = r0 > 0 && b2_supported(c, probe);
+    probe.n = Fa; probe.r = (int)r1;
+    const bool lean1 = r1 > 0 && b2_supported(c, probe) && (r0 > 0 || T == 1);
     if (r0 > 0 && r1 > 0) {
-        // time axis on (T,F) samples; flags are read from, and the outputs written
-        // to, the (F,T) layout directly, so no separate transposes are needed
+        // time axis: flags are read from the (F,T) layout; the pair goes to (T,F)
+        // when the lean frequency kernel follows, else to (F,T)
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
-        a.data = data_TF; a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
+        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = lean1 ? 0 : 1;
         a.vout = w.v_FT; a.wout = w.w_FT;
-        TC_TRY(launch_box_filter(c, a));
+        if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
+        else { a.data = data_TF; TC_TRY(launch_box_filter(c, a)); }
         memset(&a, 0, sizeof(a));
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
         a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
-        a.data = w.v_FT; a.win = w.w_FT; a.vout = out_FT; a.data2 = data_FT;
-        TC_TRY(launch_box_filter(c, a));
+        a.data = w.v_FT; a.win = w.w_FT; a.vout = out_FT;
+        if (lean1) { a.data2 = data_TF; TC_TRY(launch_box_filter2(c, a)); }
+        else { a.data2 = data_FT; TC_TRY(launch_box_filter(c, a)); }
     } else if (r0 > 0) {
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
-        a.data = data_TF; a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
+        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
         a.vout = out_FT;
-        TC_TRY(launch_box_filter(c, a));
+        if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
+        else { a.data = data_TF; TC_TRY(launch_box_filter(c, a)); }
         if (resid) {
             TC_LAUNCH_NOSYNC(k_abs_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, out_FT, out_FT, N);
             c->launches++;
@@ -103,7 +117,9 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
         a.mode_in = FIN_MASKED; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
         a.data = data_FT; a.flags = w.fl_FT; a.vout = out_FT; a.data2 = data_FT;
-        TC_TRY(launch_box_filter(c, a));
+        // T == 1: both layouts coincide and the lines are contiguous
+        if (lean1) TC_TRY(launch_box_filter2(c, a));
+        else TC_TRY(launch_box_filter(c, a));
     } else {
         TC_LAUNCH_NOSYNC(k_masked_copy, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, w.fl_FT, N,
                          resid ? FOUT_RESID : FOUT_BG, data_FT, out_FT);

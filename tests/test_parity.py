@@ -290,6 +290,22 @@ def test_masked_gaussian_filter_radii(backend):
         o2 = np.zeros_like(d)
         oracle.masked_gaussian_filter(d, fl, sig, o2)
         assert_same(o, o2, "masked filter radii (%d, %d) shape %s" % (r0, r1, shape))
+    # thread-per-line kernels: n % 16 == 0, every small radius (ring phases 2r mod 4)
+    t4 = [(r0, 4 + r0 % 3) for r0 in (2, 3, 4, 5, 6, 7, 8, 9, 11, 14)] + [(3, 2), (6, 3), (5, 5)]
+    if big(backend):
+        t4 += [(r0, r0 + 2) for r0 in (16, 21, 22, 28, 31, 32, 36)]
+    for i, (r0, r1) in enumerate(t4):
+        shape = [(160, 96), (64, 272)][i % 2] if big(backend) else [(16, 40), (32, 24)][i % 2]
+        sig = np.array((_sigma_for_radius(r0), _sigma_for_radius(r1)))
+        d = (rs.uniform(size=shape) * 10 ** rs.uniform(-2, 2, shape)).astype(np.float32)
+        d[rs.uniform(size=shape) < 0.01] = 0
+        fl = rs.uniform(size=shape) < 0.3
+        fl[shape[0] // 4:shape[0] // 2, 2:shape[1] // 2] = True
+        o = np.zeros_like(d)
+        G.masked_gaussian_filter(d, fl, sig, o)
+        o2 = np.zeros_like(d)
+        oracle.masked_gaussian_filter(d, fl, sig, o2)
+        assert_same(o, o2, "masked filter (thread per line) radii (%d, %d) shape %s" % (r0, r1, shape))
 
 
 def test_get_background2d(backend):

@@ -94,8 +94,10 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
         a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = lean1 ? 0 : 1;
         a.vout = w.v_FT; a.wout = w.w_FT;
-        if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
-        else { a.data = data_TF; TC_TRY(launch_box_filter(c, a)); }
+        a.data = data_TF;
+        if (t4a_supported(c, a)) TC_TRY(launch_box_t4a(c, a));
+        else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
+        else TC_TRY(launch_box_filter(c, a));
         memset(&a, 0, sizeof(a));
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
         a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;

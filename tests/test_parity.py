@@ -389,6 +389,20 @@ def test_combine_and_unaverage(backend):
         oracle._unaverage_freq(tmp, fe, af, 0.6, 0.8, want)
         got = G._combine_and_unaverage(sf, tf, ff, te, fe, af, 0.6, 0.8, F0)
         assert_same(got, want, "combine te=%d fe=%d af=%d" % (te, fe, af))
+    # 16-flags-per-thread kernels (average_freq == 1, F % 16 == 0), incl. the row / column rules
+    for T2, F2, te, fe, ft, ff2 in ((30, 48, 3, 3, 0.6, 0.8), (7, 96, 4, 5, 0.3, 0.2), (40, 32, 1, 1, 0.1, 0.5),
+                                    (300, 64, 2, 16, 0.05, 0.3), (9, 16, 0, 0, 0.6, 0.8), (5, 80, 6, 9, 0.9, 0.1)):
+        sf = rs.uniform(size=(1, F2)) < 0.1
+        tf = rs.uniform(size=(T2, F2)) < 0.05
+        ff = rs.uniform(size=(T2, F2)) < 0.05
+        tf[T2 // 2, :F2 - 3] = True
+        ff[:T2 - 2, 7] = True
+        tmp = np.zeros((T2, F2), bool)
+        oracle._combine_flags(sf, tf, ff, oracle._as_min_dtype(te), tmp)
+        want = np.zeros((T2, F2), bool)
+        oracle._unaverage_freq(tmp, fe, 1, ft, ff2, want)
+        got = G._combine_and_unaverage(sf, tf, ff, te, fe, 1, ft, ff2, F2)
+        assert_same(got, want, "combine v16 T=%d F=%d te=%d fe=%d" % (T2, F2, te, fe))
 
 
 def _st_cases(backend):

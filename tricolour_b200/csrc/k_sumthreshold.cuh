@@ -530,6 +530,138 @@ k_finalize_flags(const u8 *__restrict__ d, const int *__restrict__ rowcnt,
     if (iter_flags && fl) iter_flags[i] = 1;
 }
 
+// ----------------------------------------------------------------------------
+// 16-bytes-per-thread forms of the three kernels above for average_freq == 1 and
+// F % 16 == 0 (flag bytes are 0/1 throughout, so bytewise OR is the logical OR
+// and a popcount of a word is the number of set flags in it).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 tc_or4(uint4 a, uint4 b)
+{
+    return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+}
+
+// c1 = ext > 0 ? spec | OR over the time window of (time | freq) : 0
+__global__ void __launch_bounds__(256)
+k_combine_time_v16(const uint4 *__restrict__ spec, const uint4 *__restrict__ time_f,
+                   const uint4 *__restrict__ freq_f, int64_t total16, int T, int F16, int lo, int ext,
+                   uint4 *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total16) return;
+    int64_t row = i / F16;
+    int f = (int)(i - row * F16);
+    int64_t cp = row / T;
+    int t = (int)(row - cp * T);
+    uint4 any = make_uint4(0u, 0u, 0u, 0u);
+    if (ext > 0) {
+        any = spec[cp * F16 + f];
+        int t0 = t + lo < 0 ? 0 : t + lo;
+        int t1 = t + lo + ext > T ? T : t + lo + ext;
+        for (int tt = t0; tt < t1; tt++) {
+            int64_t k = (cp * T + tt) * (int64_t)F16 + f;
+            any = tc_or4(any, tc_or4(time_f[k], freq_f[k]));
+        }
+    }
+    out[i] = any;
+}
+
+// d[t, f] = OR over [f + lo, f + lo + ext) of c1[t, .]; rowcnt[row] = number of
+// set d in the row (before the row rule).  One block per row, the row (plus 16
+// zero bytes on either side) staged in shared memory as words.
+__global__ void __launch_bounds__(256)
+k_dilate_rows_v16(const uint4 *__restrict__ c1, int F16, int lo, int ext, uint4 *__restrict__ d,
+                  int *__restrict__ rowcnt)
+{
+    TC_DYN_SMEM(unsigned, row);          // [4 pad][F/4][4 pad] words
+    __shared__ int s_cnt;
+    const int64_t r = blockIdx.x;
+    const int nw = F16 * 4;
+    if (threadIdx.x == 0) s_cnt = 0;
+    if (threadIdx.x < 4) { row[threadIdx.x] = 0u; row[4 + nw + threadIdx.x] = 0u; }
+    for (int v = threadIdx.x; v < F16; v += blockDim.x) {
+        uint4 q = c1[r * F16 + v];
+        row[4 + 4 * v] = q.x; row[5 + 4 * v] = q.y; row[6 + 4 * v] = q.z; row[7 + 4 * v] = q.w;
+    }
+    __syncthreads();
+    int local = 0;
+    for (int v = threadIdx.x; v < F16; v += blockDim.x) {
+        unsigned o[4] = {0u, 0u, 0u, 0u};
+        for (int sft = lo; sft < lo + ext; sft++) {
+            // bytes [16 v + sft, 16 v + sft + 16) of the row; |sft| < 16 keeps it inside the padding
+            const int b0 = 16 * v + sft + 16;          // byte offset in the padded buffer
+            const int w0 = b0 >> 2, sh = (b0 & 3) * 8;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned a = row[w0 + q], b = row[w0 + q + 1];
+                o[q] |= sh ? ((a >> sh) | (b << (32 - sh))) : a;
+            }
+        }
+        d[r * F16 + v] = make_uint4(o[0], o[1], o[2], o[3]);
+        local += __popc(o[0]) + __popc(o[1]) + __popc(o[2]) + __popc(o[3]);
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(TC_FULL_MASK, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcnt[r] = s_cnt;
+}
+
+// colcnt[cp, f] = number of set d[cp, :, f]; one thread per word (4 channels)
+__global__ void __launch_bounds__(128)
+k_colcnt_v4(const unsigned *__restrict__ d, int T, int F4, int64_t total4, int *__restrict__ colcnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int64_t cp = i / F4;
+    int f = (int)(i - cp * F4);
+    const unsigned *p = d + cp * (int64_t)T * F4 + f;
+    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int t0 = 0; t0 < T; t0 += 128) {
+        unsigned acc = 0u;                     // four byte counters, at most 128 each
+        const int t1 = t0 + 128 < T ? t0 + 128 : T;
+        for (int t = t0; t < t1; t++) acc += p[(int64_t)t * F4];
+        c0 += acc & 0xffu; c1 += (acc >> 8) & 0xffu; c2 += (acc >> 16) & 0xffu; c3 += acc >> 24;
+    }
+    reinterpret_cast<int4 *>(colcnt)[i] = make_int4((int)c0, (int)c1, (int)c2, (int)c3);
+}
+
+// out = d | row rule | column rule | isnan(input), four samples per thread
+__global__ void __launch_bounds__(256)
+k_finalize_flags_v4(const unsigned *__restrict__ d, const int *__restrict__ rowcnt,
+                    const int4 *__restrict__ colcnt, const void *__restrict__ vis, int vis_kind,
+                    int64_t total4, int T, int F4, double row_limit, double col_limit,
+                    unsigned *__restrict__ out, unsigned *__restrict__ iter_flags)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    int64_t row = i / F4;
+    int f = (int)(i - row * F4);
+    int64_t cp = row / T;
+    unsigned w = d[i];
+    if ((double)rowcnt[row] > row_limit) w = 0x01010101u;
+    const int4 cc = colcnt[cp * F4 + f];
+    if ((double)cc.x > col_limit) w |= 0x1u;
+    if ((double)cc.y > col_limit) w |= 0x100u;
+    if ((double)cc.z > col_limit) w |= 0x10000u;
+    if ((double)cc.w > col_limit) w |= 0x1000000u;
+    if (vis) {
+        if (vis_kind == TC_VIS_COMPLEX64) {
+            const float4 a = ((const float4 *)vis)[2 * i], b = ((const float4 *)vis)[2 * i + 1];
+            if (a.x != a.x || a.y != a.y) w |= 0x1u;
+            if (a.z != a.z || a.w != a.w) w |= 0x100u;
+            if (b.x != b.x || b.y != b.y) w |= 0x10000u;
+            if (b.z != b.z || b.w != b.w) w |= 0x1000000u;
+        } else {
+            const float4 a = ((const float4 *)vis)[i];
+            if (a.x != a.x) w |= 0x1u;
+            if (a.y != a.y) w |= 0x100u;
+            if (a.z != a.z) w |= 0x10000u;
+            if (a.w != a.w) w |= 0x1000000u;
+        }
+    }
+    out[i] = w;
+    if (iter_flags && w) iter_flags[i] |= w;
+}
+
 // normalise arbitrary non-zero flag bytes to 0/1
 __global__ void __launch_bounds__(256)
 k_norm_flags(const u8 *__restrict__ in, u8 *__restrict__ out, int64_t n)

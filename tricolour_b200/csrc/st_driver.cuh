@@ -76,8 +76,9 @@ k_abs_sub(const float *a, const float *b, float *out, int64_t n)
 // the second one reads.
 static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const float *data_TF,
                              const float *data_FT, BgWork &w, int64_t r0, int64_t r1, int resid,
-                             float *out_FT)
+                             float *out_FT, int want_TF = 0, int *got_TF = nullptr)
 {
+    if (got_TF) *got_TF = 0;
     int64_t N = np * (int64_t)T * Fa;
     FilterArgs a;
     memset(&a, 0, sizeof(a));
@@ -102,8 +103,12 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
         a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
         a.data = w.v_FT; a.win = w.w_FT; a.vout = out_FT;
-        if (lean1) { a.data2 = data_TF; TC_TRY(launch_box_filter2(c, a)); }
-        else { a.data2 = data_FT; TC_TRY(launch_box_filter(c, a)); }
+        if (lean1) {
+            // the lean kernel can leave its output line-contiguous, i.e. in (T,F)
+            a.data2 = data_TF;
+            if (want_TF && got_TF) { a.out_transposed = 1; *got_TF = 1; }
+            TC_TRY(launch_box_filter2(c, a));
+        } else { a.data2 = data_FT; TC_TRY(launch_box_filter(c, a)); }
     } else if (r0 > 0) {
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
@@ -151,10 +156,12 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
     tc_mark mark = tc_arena_mark(c);
     TC_TRY(dev_bg_work_alloc(c, N, two_axes, &w));
     TC_CUDA(cudaMemcpyAsync(w.fl_FT, flags_FT, N, cudaMemcpyDeviceToDevice, c->stream));
+    int bg_is_TF = 0;
     for (int it = 0; it <= iterations; it++) {
         int64_t r0 = T == 1 ? 0 : radii[2 * it], r1 = radii[2 * it + 1];
         bool final_pass = it == iterations;
-        TC_TRY(dev_masked_filter(c, np, T, Fa, data_TF, data_FT, w, r0, r1, final_pass ? 0 : 1, work_FT));
+        TC_TRY(dev_masked_filter(c, np, T, Fa, data_TF, data_FT, w, r0, r1, final_pass ? 0 : 1, work_FT,
+                                 final_pass ? 1 : 0, &bg_is_TF));
         if (final_pass) break;
         ChunkSelectArgs s;
         memset(&s, 0, sizeof(s));
@@ -165,7 +172,7 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
     // _linearly_interpolate_nans along frequency for every (plane, dump): one
     // warp per contiguous (T,F) row
     const float *bg_TF = work_FT;
-    if (T != 1) {
+    if (T != 1 && !bg_is_TF) {
         float *tmp;
         TC_TRY(tc_alloc(c, (size_t)N, &tmp));
         TC_TRY(launch_transpose<float>(c, work_FT, tmp, np, Fa, T));
@@ -261,6 +268,56 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     return TC_OK;
 }
 
+// _combine_flags + _unaverage_freq + the final isnan OR (flagging.py:784-816,
+// 878-918, 776-781) for np planes; c1 is N bytes of scratch
+static int dev_combine_flags(tc_context *c, int64_t np, int T, int Fa, int F, int avg, int te, int fe,
+                             double frac_t, double frac_f, const u8 *spec_out, const u8 *time_TF,
+                             const u8 *freq_TF, u8 *c1, const void *vis, int vis_kind, u8 *out_flags,
+                             u8 *iter_flags_accum)
+{
+    const int64_t N = np * (int64_t)T * Fa, NF = np * (int64_t)T * F;
+    tc_prof_begin(c, TCP_COMBINE);
+    u8 *dflags;
+    int *rowcnt, *colcnt;
+    TC_TRY(tc_alloc(c, NF, &dflags));
+    TC_TRY(tc_alloc(c, np * (int64_t)T, &rowcnt));
+    TC_TRY(tc_alloc(c, np * (int64_t)F, &colcnt));
+    const bool vec16 = avg == 1 && (F & 15) == 0 && fe >= 0 && fe <= 16 && ((uintptr_t)vis & 15) == 0 &&
+                       ((uintptr_t)out_flags & 3) == 0 && ((uintptr_t)iter_flags_accum & 3) == 0 &&
+                       ((uintptr_t)spec_out & 15) == 0 && ((uintptr_t)time_TF & 15) == 0 &&
+                       ((uintptr_t)freq_TF & 15) == 0 && !getenv("TC_COMBINE_SCALAR");
+    if (vec16) {
+        const int F16 = F / 16, F4 = F / 4;
+        TC_LAUNCH_NOSYNC(k_combine_time_v16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (const uint4 *)spec_out,
+                         (const uint4 *)time_TF, (const uint4 *)freq_TF, N / 16, T, F16, -(te / 2), te, (uint4 *)c1);
+        c->launches++;
+        TC_LAUNCH(k_dilate_rows_v16, (unsigned)(np * T), 256, (size_t)(F + 32), c->stream, (const uint4 *)c1, F16,
+                  -(fe / 2), fe, (uint4 *)dflags, rowcnt);
+        c->launches++;
+        TC_LAUNCH_NOSYNC(k_colcnt_v4, tc_blocks_for(np * (int64_t)F4, 128), 128, 0, c->stream,
+                         (const unsigned *)dflags, T, F4, np * (int64_t)F4, colcnt);
+        c->launches++;
+        TC_LAUNCH_NOSYNC(k_finalize_flags_v4, tc_blocks_for(NF / 4, 256), 256, 0, c->stream, (const unsigned *)dflags,
+                         rowcnt, (const int4 *)colcnt, vis, vis_kind, NF / 4, T, F4, frac_f * (double)F,
+                         (double)T * frac_t, (unsigned *)out_flags, (unsigned *)iter_flags_accum);
+        c->launches++;
+    } else {
+        TC_LAUNCH_NOSYNC(k_combine_time, tc_blocks_for(N, 256), 256, 0, c->stream, spec_out, time_TF, freq_TF, N, T,
+                         Fa, -(te / 2), te, c1);
+        c->launches++;
+        TC_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * np * (size_t)F, c->stream));
+        TC_LAUNCH(k_unaverage_rows, (unsigned)(np * T), 256, 0, c->stream, c1, T, Fa, F, -(fe / 2), fe, avg, dflags,
+                  rowcnt, colcnt);
+        c->launches++;
+        TC_LAUNCH_NOSYNC(k_finalize_flags, tc_blocks_for(NF, 256), 256, 0, c->stream, dflags, rowcnt, colcnt, vis,
+                         vis_kind, NF, T, F, frac_f * (double)F, (double)T * frac_t, out_flags, iter_flags_accum);
+        c->launches++;
+    }
+    tc_prof_end(c);
+    TC_KERNEL_CHECK();
+    return TC_OK;
+}
+
 // ----------------------------------------------------------------------------
 // one _get_flags_impl pass over np planes
 // ----------------------------------------------------------------------------
@@ -346,25 +403,8 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     // _combine_flags + _unaverage_freq + final isnan OR
     u8 *c1 = fl_FT;  // fl_FT is no longer needed
     int te = (int)p->time_extend, fe = (int)p->freq_extend;
-    tc_prof_begin(c, TCP_COMBINE);
-    TC_LAUNCH_NOSYNC(k_combine_time, tc_blocks_for(N, 256), 256, 0, c->stream, spec_out, time_TF, freq_TF, N, T,
-                     Fa, -(te / 2), te, c1);
-    c->launches++;
-    u8 *dflags;
-    int *rowcnt, *colcnt;
-    TC_TRY(tc_alloc(c, NF, &dflags));
-    TC_TRY(tc_alloc(c, np * (int64_t)T, &rowcnt));
-    TC_TRY(tc_alloc(c, np * (int64_t)F, &colcnt));
-    TC_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * np * (size_t)F, c->stream));
-    TC_LAUNCH(k_unaverage_rows, (unsigned)(np * T), 256, 0, c->stream, c1, T, Fa, F, -(fe / 2), fe, avg, dflags,
-              rowcnt, colcnt);
-    c->launches++;
-    TC_LAUNCH_NOSYNC(k_finalize_flags, tc_blocks_for(NF, 256), 256, 0, c->stream, dflags, rowcnt, colcnt, vis,
-                     vis_kind, NF, T, F, p->flag_all_freq_frac * (double)F, (double)T * p->flag_all_time_frac,
-                     out_flags, iter_flags_accum);
-    tc_prof_end(c);
-    c->launches++;
-    TC_KERNEL_CHECK();
+    TC_TRY(dev_combine_flags(c, np, T, Fa, F, avg, te, fe, p->flag_all_time_frac, p->flag_all_freq_frac, spec_out,
+                             time_TF, freq_TF, c1, vis, vis_kind, out_flags, iter_flags_accum));
     tc_arena_release(c, pass_mark);
     return TC_OK;
 }

@@ -692,26 +692,13 @@ int tc_stage_combine_unaverage(tc_context *c, const uint8_t *spec, const uint8_t
     TC_TRY(tc_stage_in(c, spec, (size_t)(ncp * Fa), space, &ds));
     TC_TRY(tc_stage_in(c, time_f, (size_t)N, space, &dt));
     TC_TRY(tc_stage_in(c, freq_f, (size_t)N, space, &df));
-    u8 *c1, *dfl, *dout;
-    int *rowcnt, *colcnt;
+    u8 *c1, *dout;
     TC_TRY(tc_alloc(c, (size_t)N, &c1));
-    TC_TRY(tc_alloc(c, (size_t)NF, &dfl));
-    TC_TRY(tc_alloc(c, (size_t)(ncp * T), &rowcnt));
-    TC_TRY(tc_alloc(c, (size_t)(ncp * F), &colcnt));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)NF, space, &dout));
-    if (NF) {
-        int te = (int)time_extend, fe = (int)freq_extend;
-        TC_LAUNCH_NOSYNC(k_combine_time, tc_blocks_for(N, 256), 256, 0, c->stream, ds, dt, df, N, (int)T, (int)Fa,
-                         -(te / 2), te, c1);
-        TC_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * (size_t)(ncp * F), c->stream));
-        TC_LAUNCH(k_unaverage_rows, (unsigned)(ncp * T), 256, 0, c->stream, c1, (int)T, (int)Fa, (int)F, -(fe / 2), fe,
-                  (int)average_freq, dfl, rowcnt, colcnt);
-        TC_LAUNCH_NOSYNC(k_finalize_flags, tc_blocks_for(NF, 256), 256, 0, c->stream, dfl, rowcnt, colcnt,
-                         (const void *)nullptr, 0, NF, (int)T, (int)F, flag_all_freq_frac * (double)F,
-                         (double)T * flag_all_time_frac, dout, (u8 *)nullptr);
-        c->launches += 3;
-        TC_KERNEL_CHECK();
-    }
+    if (NF)
+        TC_TRY(dev_combine_flags(c, ncp, (int)T, (int)Fa, (int)F, (int)average_freq, (int)time_extend,
+                                 (int)freq_extend, flag_all_time_frac, flag_all_freq_frac, ds, dt, df, c1,
+                                 (const void *)nullptr, 0, dout, (u8 *)nullptr));
     return tc_stage_out_end(c, out, dout, (size_t)NF, space);
 }
 

@@ -397,6 +397,126 @@ __device__ __forceinline__ void st_fused_1248(const float *__restrict__ d, u8 *_
     }
 }
 
+// Branch-free form of the single-sweep scan (same window lags, same per-window
+// arithmetic, so the flags are identical).  Differences from st_fused_1248:
+//   * the line is cut into blocks of 8 steps; interior blocks (every window
+//     inside the line, every output inside the chunk) carry no predicates;
+//   * "x > limit" on a float32 sample is decided in float32 against the
+//     smallest float32 above the float64 limit (exactly the same predicate);
+//   * avg * (-scale) > limit is evaluated as avg * scale < -limit (the product
+//     only changes sign), one multiply per window instead of two;
+//   * the pos / neg smear is a 2-bit-per-step shift register instead of "last
+//     flagged start" indices;
+//   * loads and stores walk pointers instead of recomputing 64-bit indices.
+struct St2Win {
+    double c;        // running prefix sum (cum[i + 1])
+    unsigned h;      // bit 2q: the window that started q steps ago exceeded +limit; bit 2q+1: -limit
+    double limit, sc;
+    float hif;       // smallest float32 > limit (NaN when there is none)
+};
+
+__device__ __forceinline__ float st2_float_above(double limit)
+{
+    // smallest float32 f with (double)f > limit
+    if (!(limit < 3.0e38)) return NAN;              // inf / NaN limits never clamp
+    float f = __double2float_rn(limit);
+    if (!((double)f > limit)) f = __uint_as_float(__float_as_uint(f) + 1u);   // limit >= 0: next float up
+    if (!((double)f > limit)) f = __uint_as_float(__float_as_uint(f) + 1u);
+    return f;
+}
+
+template <int W, bool INTERIOR>
+__device__ __forceinline__ unsigned st2_step(St2Win &w, double *ring, int slot, float xf, unsigned st, int j, int nj)
+{
+    // processes sample i = j + W - 1 and returns the pos/neg bits that window
+    // coverage adds to sample j.  nj = number of window starts (m - W + 1)
+    const double xd = (double)xf;
+    double x1 = xd;
+    if (W > 1) {
+        const bool ph = (st & 1u) && xf >= w.hif;
+        const bool pl = (st & 2u) && xf <= -w.hif;
+        x1 = ph ? w.limit : (pl ? -w.limit : xd);
+    }
+    w.c = w.c + x1;
+    const double cj = ring[slot];
+    ring[slot] = w.c;
+    const double avg = w.c - cj;
+    const double t = W == 1 ? avg : avg * w.sc;
+    const bool ok = INTERIOR || ((unsigned)j < (unsigned)nj);
+    const bool pos = ok && t > w.limit;
+    const bool neg = ok && t < -w.limit;
+    w.h = (w.h << 2) | (pos ? 1u : 0u) | (neg ? 2u : 0u);
+    const unsigned MP = W == 1 ? 0x1u : (W == 2 ? 0x5u : (W == 4 ? 0x55u : 0x5555u));
+    return ((w.h & MP) ? 1u : 0u) | ((w.h & (MP << 1)) ? 2u : 0u);
+}
+
+__device__ __forceinline__ void st_fused_1248_v2(const float *__restrict__ d, u8 *__restrict__ out, int m, int rel,
+                                                 int nout, int64_t es, float thr, const double *tf,
+                                                 const float *scale)
+{
+    St2Win w0, w1, w2, w3;
+    w0.limit = (double)thr / tf[0]; w1.limit = (double)thr / tf[1];
+    w2.limit = (double)thr / tf[2]; w3.limit = (double)thr / tf[3];
+    w0.sc = (double)scale[0]; w1.sc = (double)scale[1]; w2.sc = (double)scale[2]; w3.sc = (double)scale[3];
+    w0.hif = st2_float_above(w0.limit); w1.hif = st2_float_above(w1.limit);
+    w2.hif = st2_float_above(w2.limit); w3.hif = st2_float_above(w3.limit);
+    w0.c = w1.c = w2.c = w3.c = 0.0;
+    w0.h = w1.h = w2.h = w3.h = 0u;
+    const int nj0 = m, nj1 = m - 1 > 0 ? m - 1 : 0, nj2 = m - 3 > 0 ? m - 3 : 0, nj3 = m - 7 > 0 ? m - 7 : 0;
+    double h0[1] = {0.0}, h1[2] = {0.0, 0.0}, h2[4] = {0.0, 0.0, 0.0, 0.0}, h3[8];
+    float xr[8];             // x[s - q] in xr[(s - q) & 7]
+    unsigned p0prev = 0u;    // pn_0(s - 1)
+    unsigned p1r[4];         // pn_1(j) in p1r[j & 3]
+    unsigned p2r[8];         // pn_2(j) in p2r[j & 7]
+#pragma unroll
+    for (int k = 0; k < 8; k++) { h3[k] = 0.0; xr[k] = 0.f; p2r[k] = 0u; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) p1r[k] = 0u;
+    const float *pd = d;                              // sample s
+    u8 *po = out + (int64_t)(-11 - rel) * es;         // output of sample j = s - 11 (only dereferenced in range)
+    const int nsteps = m + 11;
+    // window starts at step s: j0 = s, j1 = s - 1, j2 = s - 4, j3 = s - 11
+    for (int s0 = 0; s0 < nsteps; s0 += 8) {
+        // interior: all starts valid for the whole block, all 8 outputs inside the chunk
+        const bool interior = s0 >= 11 + rel && s0 + 7 < nj3 && s0 + 7 - 11 - rel < nout;
+        if (interior) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float xs = *pd;
+                pd += es;
+                xr[k] = xs;
+                const unsigned p0 = st2_step<1, true>(w0, h0, 0, xs, 0u, 0, 0);
+                const unsigned a1 = st2_step<2, true>(w1, h1, k & 1, xs, p0, 0, 0);
+                p1r[(k + 3) & 3] = p0prev | a1;
+                p0prev = p0;
+                const unsigned a2 = st2_step<4, true>(w2, h2, (k + 3) & 3, xr[(k + 7) & 7], p1r[(k + 3) & 3], 0, 0);
+                p2r[(k + 4) & 7] = p1r[k & 3] | a2;
+                const unsigned a3 = st2_step<8, true>(w3, h3, (k + 4) & 7, xr[(k + 4) & 7], p2r[(k + 4) & 7], 0, 0);
+                *po = (p2r[(k + 5) & 7] | a3) ? 1 : 0;
+                po += es;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int s = s0 + k;
+                const float xs = s < m ? *pd : 0.f;
+                pd += es;
+                xr[k] = xs;
+                const unsigned p0 = st2_step<1, false>(w0, h0, 0, xs, 0u, s, nj0);
+                const unsigned a1 = st2_step<2, false>(w1, h1, k & 1, xs, p0, s - 1, nj1);
+                p1r[(k + 3) & 3] = p0prev | a1;
+                p0prev = p0;
+                const unsigned a2 = st2_step<4, false>(w2, h2, (k + 3) & 3, xr[(k + 7) & 7], p1r[(k + 3) & 3], s - 4, nj2);
+                p2r[(k + 4) & 7] = p1r[k & 3] | a2;
+                const unsigned a3 = st2_step<8, false>(w3, h3, (k + 4) & 7, xr[(k + 4) & 7], p2r[(k + 4) & 7], s - 11, nj3);
+                const int o = s - 11 - rel;
+                if ((unsigned)o < (unsigned)nout && s - 11 < m) *po = (p2r[(k + 5) & 7] | a3) ? 1 : 0;
+                po += es;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_st_scan(StScanArgs a)
 {
@@ -423,6 +543,10 @@ k_st_scan(StScanArgs a)
     const int64_t es = a.estride, ss = a.ninner;
     float thr = a.thr[line * a.nchunks + chunk];
 
+    if (a.fused1248 == 2) {
+        st_fused_1248_v2(d, o, m, c0 - p0, c1 - c0, es, thr, a.tf, a.scale);
+        return;
+    }
     if (a.fused1248) {
         st_fused_1248(d, o, m, c0 - p0, c1 - c0, es, thr, a.tf, a.scale);
         return;
@@ -445,6 +569,85 @@ k_st_scan(StScanArgs a)
     const u8 *pn = pin;
     int rel = c0 - p0;
     for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = (pn && pn[(int64_t)(rel + i) * ss]) ? 1 : 0;
+}
+
+// General window lists whose prefix ring fits shared memory: same sweeps as
+// st_window_mem, but cum[i + 1 - w] comes from a w-deep ring of float64 prefixes
+// per thread in shared memory ([slot][thread]) instead of a global scratch plane.
+__device__ __forceinline__ void st_window_ring(const float *__restrict__ d, const u8 *__restrict__ pin,
+                                               u8 *__restrict__ pout, double *ring, int bs, int m, int w,
+                                               int64_t es, int64_t ss, double limit, double sc, double nsc)
+{
+    for (int k = 0; k < w; k++) ring[k * bs] = 0.0;
+    double c = 0.0;
+    int slot = 0;
+    int lastpos = -(1 << 30), lastneg = -(1 << 30);
+    const float *pd = d;
+    const u8 *pi = pin;
+    u8 *po = pout - (int64_t)(w - 1) * ss;     // state of sample j = i + 1 - w
+    const u8 *pj = pin ? pin - (int64_t)(w - 1) * ss : nullptr;
+    for (int i = 0; i < m; i++) {
+        double x = (double)*pd;
+        const u8 st = pi ? *pi : (u8)0;
+        if ((st & 1) && x > limit) x = limit;
+        else if ((st & 2) && x < -limit) x = -limit;
+        c = c + x;
+        slot++; if (slot >= w) slot = 0;
+        const double cj = ring[slot * bs];
+        ring[slot * bs] = c;
+        const int j = i + 1 - w;
+        if (j >= 0) {
+            const double avg = c - cj;
+            if (avg * sc > limit) lastpos = j;
+            if (avg * nsc > limit) lastneg = j;
+            const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+            const u8 sj = pj ? *pj : (u8)0;
+            *po = (u8)(sj | add);
+        }
+        pd += es; po += ss;
+        if (pi) { pi += ss; pj += ss; }
+    }
+    int jt = m - w + 1; if (jt < 0) jt = 0;
+    for (int j = jt; j < m; j++) {
+        const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+        const u8 sj = pin ? pin[(int64_t)j * ss] : (u8)0;
+        pout[(int64_t)j * ss] = (u8)(sj | add);
+    }
+}
+
+__global__ void __launch_bounds__(64)
+k_st_scan_ring(StScanArgs a)
+{
+    TC_DYN_SMEM(double, rings);
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nlines * a.nchunks) return;
+    int64_t per_plane = (int64_t)a.nchunks * a.ninner;
+    int64_t plane = g / per_plane;
+    int64_t rem = g - plane * per_plane;
+    int chunk = (int)(rem / a.ninner);
+    int64_t inner = rem - (int64_t)chunk * a.ninner;
+    int64_t line = plane * a.ninner + inner;
+    int c0 = (int)a.chunk_ends[chunk], c1 = (int)a.chunk_ends[chunk + 1];
+    int p0 = c0 - a.maxw + 1; if (p0 < 0) p0 = 0;
+    int p1 = c1 + a.maxw - 1; if (p1 > a.n) p1 = a.n;
+    int m = p1 - p0;
+    const float *d = a.data + plane * a.outer_stride + inner + (int64_t)p0 * a.estride;
+    u8 *o = a.out + plane * a.outer_stride + inner + (int64_t)c0 * a.estride;
+    int64_t pbase = ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
+    u8 *pa = a.pn + pbase, *pb = a.pn2 + pbase;
+    const int64_t es = a.estride, ss = a.ninner;
+    float thr = a.thr[line * a.nchunks + chunk];
+    const u8 *pin = nullptr;
+    u8 *pout = pa;
+    for (int wi = 0; wi < a.nwin; wi++) {
+        const int w = (int)a.windows[wi];
+        st_window_ring(d, pin, pout, rings + threadIdx.x, (int)blockDim.x, m, w, es, ss, (double)thr / a.tf[wi],
+                       (double)a.scale[wi], (double)(-a.scale[wi]));
+        pin = pout;
+        pout = (pout == pa) ? pb : pa;
+    }
+    int rel = c0 - p0;
+    for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = pin[(int64_t)(rel + i) * ss] ? 1 : 0;
 }
 
 // ----------------------------------------------------------------------------

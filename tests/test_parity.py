@@ -440,6 +440,22 @@ def test_sum_threshold_flagger(backend):
         tb.sum_threshold_flagger(vis, flags, average_freq=2)   # window 0, as in the reference
 
 
+def test_sum_threshold_flagger_aligned(backend):
+    """shapes with T % 16 == 0 and F % 16 == 0 take the vectorised / thread-per-line kernels"""
+    shape = (2, 2, 64, 256) if big(backend) else (1, 1, 32, 64)
+    vis, flags = common.make_windows(*shape, seed=27)
+    cases = [dict(num_major_iterations=1, background_iterations=2),
+             dict(num_major_iterations=1, background_iterations=1, spike_width_time=2, spike_width_freq=4.0,
+                  time_extend=4, freq_extend=5, flag_all_time_frac=0.3, flag_all_freq_frac=0.4)]
+    if big(backend):
+        cases += [dict(common.DEFAULT_STRATEGY_KW["background_flags"], num_major_iterations=2),
+                  dict(common.DEFAULT_STRATEGY_KW["final_st_very_broad"])]
+    for kw in cases:
+        got = tb.sum_threshold_flagger(vis, flags, **kw)
+        want = oracle.sum_threshold_flagger(vis, flags, **kw)
+        assert_same(got, want, "sum_threshold_flagger aligned %s" % (kw,))
+
+
 def test_sum_threshold_flagger_class(backend):
     shape = (3, 64, 345) if big(backend) else (1, 20, 90)
     rs = np.random.RandomState(11)

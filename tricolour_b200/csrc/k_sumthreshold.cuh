@@ -57,6 +57,32 @@ k_or_spec(u8 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total, in
     if (spec[cp * Fa + f]) flags[i] = 1;
 }
 
+// 16 flags per thread; layout (cp, T, Fa) with Fa % 16 == 0
+__global__ void __launch_bounds__(256)
+k_or_spec_tf16(uint4 *__restrict__ flags, const uint4 *__restrict__ spec, int64_t total16, int T, int F16)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total16) return;
+    int64_t row = i / F16;
+    int f = (int)(i - row * F16);
+    int64_t cp = row / T;
+    const uint4 sp = spec[cp * F16 + f];
+    if (sp.x | sp.y | sp.z | sp.w) {
+        uint4 v = flags[i];
+        v.x |= sp.x; v.y |= sp.y; v.z |= sp.z; v.w |= sp.w;
+        flags[i] = v;
+    }
+}
+
+// the same on the transposed layout (cp, Fa, T) with T % 16 == 0: one spectrum flag per row of T
+__global__ void __launch_bounds__(256)
+k_or_spec_ft16(uint4 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total16, int T16)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total16) return;
+    if (spec[i / T16]) flags[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+}
+
 // out = a - b elementwise
 __global__ void __launch_bounds__(256)
 k_sub(const float *a, const float *b, float *out, int64_t n)

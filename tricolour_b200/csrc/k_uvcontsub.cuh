@@ -44,15 +44,29 @@ k_uv_mean(const float2 *__restrict__ vis, const u8 *__restrict__ flags, int T, i
     if (f < F) {
         float sr = 0.f, si = 0.f;
         int cnt = 0;
-        for (int t = 0; t < T; t++) {
-            int64_t i = (cp * T + t) * (int64_t)F + f;
-            if (flags[i]) continue;
-            nun++;
-            float2 v = vis[i];
-            if (v.x != v.x || v.y != v.y) continue;
-            sr = __fadd_rn(sr, v.x);
-            si = __fadd_rn(si, v.y);
-            cnt++;
+        // eight dumps per trip so that the loads of a trip are all in flight together;
+        // the sums stay sequential in t
+        const float2 *pv = vis + (cp * T) * (int64_t)F + f;
+        const u8 *pf = flags + (cp * T) * (int64_t)F + f;
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            float2 v[8];
+            u8 fl[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const bool in = t0 + k < T;
+                fl[k] = in ? pf[(int64_t)k * F] : (u8)1;
+                v[k] = in ? pv[(int64_t)k * F] : make_float2(0.f, 0.f);
+            }
+            pv += 8 * (int64_t)F; pf += 8 * (int64_t)F;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (fl[k]) continue;
+                nun++;
+                if (v[k].x != v[k].x || v[k].y != v[k].y) continue;
+                sr = __fadd_rn(sr, v[k].x);
+                si = __fadd_rn(si, v[k].y);
+                cnt++;
+            }
         }
         float2 o = make_float2(0.f, 0.f);
         if (cnt > 0) {

@@ -21,7 +21,7 @@
 static int dev_upload_i64(tc_context *c, const int64_t *h, size_t n, int64_t **d)
 {
     TC_TRY(tc_alloc(c, n, d));
-    TC_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    TC_TRY(tc_upload_small(c, h, n * sizeof(int64_t), *d));
     return TC_OK;
 }
 
@@ -383,10 +383,20 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
                              p->windows_freq, p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
                              p->freq_chunk_ends, nce, spec_out));
     // flags |= spec_flags (flagging.py:954), both layouts
-    TC_LAUNCH_NOSYNC(k_or_spec, tc_blocks_for(N, 256), 256, 0, c->stream, fl_TF, spec_out, N, T, Fa);
-    c->launches++;
-    TC_KERNEL_CHECK();
-    TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+    if ((Fa & 15) == 0 && (T & 15) == 0) {
+        // flag bytes are 0/1 (k_prep wrote them): OR whole vectors, in both layouts
+        TC_LAUNCH_NOSYNC(k_or_spec_tf16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (uint4 *)fl_TF,
+                         (const uint4 *)spec_out, N / 16, T, Fa / 16);
+        TC_LAUNCH_NOSYNC(k_or_spec_ft16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (uint4 *)fl_FT, spec_out,
+                         N / 16, T / 16);
+        c->launches += 2;
+        TC_KERNEL_CHECK();
+    } else {
+        TC_LAUNCH_NOSYNC(k_or_spec, tc_blocks_for(N, 256), 256, 0, c->stream, fl_TF, spec_out, N, T, Fa);
+        c->launches++;
+        TC_KERNEL_CHECK();
+        TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+    }
 
     // 2-D background (flagging.py:957-961)
     float *bg_FT, *dres_TF;

@@ -64,6 +64,15 @@ struct tc_context {
     std::vector<ProfRec> prof_recs;
     double prof_ms[32] = {0};
     long long prof_cnt[32] = {0};
+    // page-locked staging slabs for the small host tables a call uploads (chunk
+    // boundaries, range tables, masks): copies from pageable memory would make
+    // the host wait for the stream and serialise callers that use several streams
+    enum { NSLAB = 4, SLAB_BYTES = 512 * 1024 };
+    char *slab[NSLAB] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t slab_ev[NSLAB] = {nullptr, nullptr, nullptr, nullptr};
+    bool slab_busy[NSLAB] = {false, false, false, false};
+    int slab_cur = 0;
+    size_t slab_off = 0;
 };
 
 enum { TCP_BOX_FILTER = 0, TCP_CHUNK_SELECT, TCP_LINE_MEDIAN, TCP_ST_SCAN, TCP_TRANSPOSE, TCP_PREP,
@@ -112,6 +121,49 @@ static inline void tc_prof_collect(tc_context *c)
 }
 
 static inline size_t tc_align(size_t n, size_t a = 256) { return (n + a - 1) / a * a; }
+
+// start of an API call: retire the staging slab of the previous call and move on
+static inline void tc_slab_rotate(tc_context *c)
+{
+#ifndef TC_EMU
+    if (c->slab_off && c->slab[c->slab_cur]) {
+        if (!c->slab_ev[c->slab_cur]) cudaEventCreateWithFlags(&c->slab_ev[c->slab_cur], cudaEventDisableTiming);
+        cudaEventRecord(c->slab_ev[c->slab_cur], c->stream);
+        c->slab_busy[c->slab_cur] = true;
+        c->slab_cur = (c->slab_cur + 1) % tc_context::NSLAB;
+    }
+    if (c->slab_busy[c->slab_cur]) {
+        cudaEventSynchronize(c->slab_ev[c->slab_cur]);
+        c->slab_busy[c->slab_cur] = false;
+    }
+#endif
+    c->slab_off = 0;
+}
+
+// host -> device copy of a small table, asynchronous with respect to the host
+static int tc_upload_small(tc_context *c, const void *h, size_t bytes, void *d)
+{
+    if (!bytes) return TC_OK;
+#ifndef TC_EMU
+    size_t need = tc_align(bytes, 16);
+    if (c->slab_off + need <= (size_t)tc_context::SLAB_BYTES) {
+        if (!c->slab[c->slab_cur]) {
+            void *p = nullptr;
+            if (cudaHostAlloc(&p, tc_context::SLAB_BYTES, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+            c->slab[c->slab_cur] = (char *)p;
+        }
+        if (c->slab[c->slab_cur]) {
+            char *stage = c->slab[c->slab_cur] + c->slab_off;
+            memcpy(stage, h, bytes);
+            c->slab_off += need;
+            TC_CUDA(cudaMemcpyAsync(d, stage, bytes, cudaMemcpyHostToDevice, c->stream));
+            return TC_OK;
+        }
+    }
+#endif
+    TC_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return TC_OK;
+}
 
 // start of an API call: if the previous call overflowed into extra blocks,
 // fold everything into one block of the peak size.

@@ -60,6 +60,12 @@ void tc_context_destroy(tc_context *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &b : c->blocks) cudaFree(b.ptr);
+#ifndef TC_EMU
+    for (int k = 0; k < tc_context::NSLAB; k++) {
+        if (c->slab[k]) cudaFreeHost(c->slab[k]);
+        if (c->slab_ev[k]) cudaEventDestroy(c->slab_ev[k]);
+    }
+#endif
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -111,6 +117,7 @@ static int tc_begin(tc_context *c)
 {
     if (!c) return tc_fail(TC_ERR_VALUE, "null context");
     TC_CUDA(cudaSetDevice(c->device));
+    tc_slab_rotate(c);
     return tc_arena_reset(c);
 }
 
@@ -145,8 +152,8 @@ static int apply_mask_common(tc_context *c, const u8 *flags, const u8 *bl_sel, c
     u8 *dsel, *dcm;
     TC_TRY(tc_alloc(c, sel.size(), &dsel));
     TC_TRY(tc_alloc(c, cm.size(), &dcm));
-    TC_CUDA(cudaMemcpyAsync(dsel, sel.data(), sel.size(), cudaMemcpyHostToDevice, c->stream));
-    TC_CUDA(cudaMemcpyAsync(dcm, cm.data(), cm.size(), cudaMemcpyHostToDevice, c->stream));
+    TC_TRY(tc_upload_small(c, sel.data(), sel.size(), dsel));
+    TC_TRY(tc_upload_small(c, cm.data(), cm.size(), dcm));
     TC_TRY(launch_apply_mask(c, dfl, dsel, dcm, mode, nbl, rows_per_bl, nchan, dout));
     return tc_stage_out_end(c, out, dout, (size_t)total, space);
 }
@@ -364,7 +371,7 @@ int tc_unpolarised_intensity(tc_context *c, const void *vis, int64_t nrowchan, i
 static int upload_i32(tc_context *c, const int32_t *h, size_t n, int32_t **d)
 {
     TC_TRY(tc_alloc(c, n ? n : 1, d));
-    if (n) TC_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (n) TC_TRY(tc_upload_small(c, h, n * sizeof(int32_t), *d));
     return TC_OK;
 }
 

@@ -22,11 +22,18 @@ __device__ __forceinline__ float key2f(uint32_t k)
 
 __device__ __forceinline__ int warp_sum_i(int v)
 {
+#ifndef TC_EMU
+    return __reduce_add_sync(TC_FULL_MASK, v);     // one REDUX instruction
+#else
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TC_FULL_MASK, v, o);
     return v;
+#endif
 }
 __device__ __forceinline__ uint32_t warp_max_u(uint32_t v)
 {
+#ifndef TC_EMU
+    return __reduce_max_sync(TC_FULL_MASK, v);
+#endif
     for (int o = 16; o > 0; o >>= 1) {
         uint32_t t = __shfl_xor_sync(TC_FULL_MASK, v, o);
         v = t > v ? t : v;
@@ -124,46 +131,38 @@ k_line_median(LineMedianArgs a)
         }
         return;
     }
-    // select rank `kth` (0-based) = upper median
-    int kth = total >> 1;
-    int remaining = kth;
+    // select rank `kth` (0-based) = upper median, one bit per round: the answer is
+    // the largest value v with |{keys < v}| <= kth.  Flagged slots hold the
+    // largest key so that they never count.
+#pragma unroll
+    for (int k = 0; k < VPL; k++)
+        if (!((valid >> k) & 1u)) key[k] = 0xffffffffu;
+    const int kth = total >> 1;
     uint32_t prefix = 0;
-    uint32_t cand = valid;  // lanes' candidates whose high bits match `prefix`
-    int ncand = total;
     for (int bit = 31; bit >= 0; bit--) {
-        int c0 = 0;
+        const uint32_t t = prefix | (1u << bit);
+        int c = 0;
 #pragma unroll
-        for (int k = 0; k < VPL; k++)
-            c0 += ((cand >> k) & 1u) & (((key[k] >> bit) & 1u) ^ 1u);
-        c0 = warp_sum_i(c0);
-        uint32_t take1 = remaining >= c0 ? 1u : 0u;
-        if (take1) { remaining -= c0; prefix |= 1u << bit; ncand -= c0; }
-        else ncand = c0;
-        uint32_t nc = 0;
-#pragma unroll
-        for (int k = 0; k < VPL; k++)
-            nc |= ((((key[k] >> bit) & 1u) == take1) ? 1u : 0u) << k;
-        cand &= nc;
-        if (ncand == 1) {
-            // a single candidate is left: it is the answer (remaining is 0)
-            uint32_t mine = 0;
-#pragma unroll
-            for (int k = 0; k < VPL; k++)
-                if ((cand >> k) & 1u) mine = key[k];
-            prefix = warp_max_u(mine);
-            break;
-        }
+        for (int k = 0; k < VPL; k++) c += key[k] < t ? 1 : 0;
+        c = warp_sum_i(c);
+        if (c <= kth) prefix = t;
     }
-    // `prefix` is the key of the upper median; `remaining` its rank among equals
+    // `prefix` is the key of the upper median; the lower one differs only when the
+    // upper median is the first of its equals
     float upper = key2f(prefix);
     float lower = upper;
-    if (!(total & 1) && remaining == 0) {
+    if (!(total & 1)) {
+        int c = 0;
         uint32_t best = 0;
 #pragma unroll
-        for (int k = 0; k < VPL; k++)
-            if (((valid >> k) & 1u) && key[k] < prefix && key[k] > best) best = key[k];
+        for (int k = 0; k < VPL; k++) {
+            const bool lt = key[k] < prefix;
+            c += lt ? 1 : 0;
+            if (lt && key[k] > best) best = key[k];
+        }
+        c = warp_sum_i(c);
         best = warp_max_u(best);
-        lower = key2f(best);
+        if (c == kth) lower = key2f(best);
     }
     double med = median_from_pair(lower, upper, total);
     float medf = (float)med;

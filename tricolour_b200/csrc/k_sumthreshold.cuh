@@ -45,6 +45,28 @@ k_prep(const void *__restrict__ vis, int vis_kind, const u8 *__restrict__ flags,
     else { out_data[o] = __fdiv_rn(sum, (float)cnt); out_flags[o] = 0; }
 }
 
+// factor == 1, complex64: four samples per thread
+__global__ void __launch_bounds__(256)
+k_prep_c64_v4(const float4 *__restrict__ vis, const unsigned *__restrict__ flags, int64_t total4,
+              float4 *__restrict__ out_data, unsigned *__restrict__ out_flags)
+{
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total4) return;
+    const float4 a = vis[2 * o], b = vis[2 * o + 1];
+    const unsigned f = flags[o];
+    float amp[4] = {tc_abs_c64(a.x, a.y), tc_abs_c64(a.z, a.w), tc_abs_c64(b.x, b.y), tc_abs_c64(b.z, b.w)};
+    unsigned of = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool bad = ((f >> (8 * k)) & 0xffu) || amp[k] != amp[k];
+        // a lone sample: sum = 0 + a, average = sum / 1
+        amp[k] = bad ? 0.0f : __fdiv_rn(__fadd_rn(0.0f, amp[k]), 1.0f);
+        of |= bad ? (1u << (8 * k)) : 0u;
+    }
+    out_data[o] = make_float4(amp[0], amp[1], amp[2], amp[3]);
+    out_flags[o] = of;
+}
+
 // flags[(cp,t,f)] |= spec[(cp,f)]   (flagging.py:954)
 __global__ void __launch_bounds__(256)
 k_or_spec(u8 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total, int T, int Fa)

@@ -339,7 +339,6 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     const int avg = (int)p->average_freq;
     const int Fa = (F + avg - 1) / avg;
     const int64_t N = np * (int64_t)T * Fa;
-    const int64_t NF = np * (int64_t)T * F;
     const int nce = p->nchunk_ends, nchunks = nce - 1;
     const int iters = p->background_iterations;
     TC_REQUIRE(nchunks >= 0, "freq_chunk_ends must not be empty");
@@ -351,8 +350,13 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_TRY(tc_alloc(c, N, &fl_TF)); TC_TRY(tc_alloc(c, N, &fl_FT));
     // S1 _average_freq
     tc_prof_begin(c, TCP_PREP);
-    TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
-                     data_TF, fl_TF);
+    if (avg == 1 && vis_kind == TC_VIS_COMPLEX64 && (N & 3) == 0 && ((uintptr_t)vis & 15) == 0 &&
+        ((uintptr_t)in_flags & 3) == 0)
+        TC_LAUNCH_NOSYNC(k_prep_c64_v4, tc_blocks_for(N / 4, 256), 256, 0, c->stream, (const float4 *)vis,
+                         (const unsigned *)in_flags, N / 4, (float4 *)data_TF, (unsigned *)fl_TF);
+    else
+        TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
+                         data_TF, fl_TF);
     tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();

@@ -619,85 +619,6 @@ k_st_scan(StScanArgs a)
     for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = (pn && pn[(int64_t)(rel + i) * ss]) ? 1 : 0;
 }
 
-// General window lists whose prefix ring fits shared memory: same sweeps as
-// st_window_mem, but cum[i + 1 - w] comes from a w-deep ring of float64 prefixes
-// per thread in shared memory ([slot][thread]) instead of a global scratch plane.
-__device__ __forceinline__ void st_window_ring(const float *__restrict__ d, const u8 *__restrict__ pin,
-                                               u8 *__restrict__ pout, double *ring, int bs, int m, int w,
-                                               int64_t es, int64_t ss, double limit, double sc, double nsc)
-{
-    for (int k = 0; k < w; k++) ring[k * bs] = 0.0;
-    double c = 0.0;
-    int slot = 0;
-    int lastpos = -(1 << 30), lastneg = -(1 << 30);
-    const float *pd = d;
-    const u8 *pi = pin;
-    u8 *po = pout - (int64_t)(w - 1) * ss;     // state of sample j = i + 1 - w
-    const u8 *pj = pin ? pin - (int64_t)(w - 1) * ss : nullptr;
-    for (int i = 0; i < m; i++) {
-        double x = (double)*pd;
-        const u8 st = pi ? *pi : (u8)0;
-        if ((st & 1) && x > limit) x = limit;
-        else if ((st & 2) && x < -limit) x = -limit;
-        c = c + x;
-        slot++; if (slot >= w) slot = 0;
-        const double cj = ring[slot * bs];
-        ring[slot * bs] = c;
-        const int j = i + 1 - w;
-        if (j >= 0) {
-            const double avg = c - cj;
-            if (avg * sc > limit) lastpos = j;
-            if (avg * nsc > limit) lastneg = j;
-            const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-            const u8 sj = pj ? *pj : (u8)0;
-            *po = (u8)(sj | add);
-        }
-        pd += es; po += ss;
-        if (pi) { pi += ss; pj += ss; }
-    }
-    int jt = m - w + 1; if (jt < 0) jt = 0;
-    for (int j = jt; j < m; j++) {
-        const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
-        const u8 sj = pin ? pin[(int64_t)j * ss] : (u8)0;
-        pout[(int64_t)j * ss] = (u8)(sj | add);
-    }
-}
-
-__global__ void __launch_bounds__(64)
-k_st_scan_ring(StScanArgs a)
-{
-    TC_DYN_SMEM(double, rings);
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.nlines * a.nchunks) return;
-    int64_t per_plane = (int64_t)a.nchunks * a.ninner;
-    int64_t plane = g / per_plane;
-    int64_t rem = g - plane * per_plane;
-    int chunk = (int)(rem / a.ninner);
-    int64_t inner = rem - (int64_t)chunk * a.ninner;
-    int64_t line = plane * a.ninner + inner;
-    int c0 = (int)a.chunk_ends[chunk], c1 = (int)a.chunk_ends[chunk + 1];
-    int p0 = c0 - a.maxw + 1; if (p0 < 0) p0 = 0;
-    int p1 = c1 + a.maxw - 1; if (p1 > a.n) p1 = a.n;
-    int m = p1 - p0;
-    const float *d = a.data + plane * a.outer_stride + inner + (int64_t)p0 * a.estride;
-    u8 *o = a.out + plane * a.outer_stride + inner + (int64_t)c0 * a.estride;
-    int64_t pbase = ((plane * a.nchunks + chunk) * (int64_t)a.mpad) * a.ninner + inner;
-    u8 *pa = a.pn + pbase, *pb = a.pn2 + pbase;
-    const int64_t es = a.estride, ss = a.ninner;
-    float thr = a.thr[line * a.nchunks + chunk];
-    const u8 *pin = nullptr;
-    u8 *pout = pa;
-    for (int wi = 0; wi < a.nwin; wi++) {
-        const int w = (int)a.windows[wi];
-        st_window_ring(d, pin, pout, rings + threadIdx.x, (int)blockDim.x, m, w, es, ss, (double)thr / a.tf[wi],
-                       (double)a.scale[wi], (double)(-a.scale[wi]));
-        pin = pout;
-        pout = (pout == pa) ? pb : pa;
-    }
-    int rel = c0 - p0;
-    for (int i = 0; i < c1 - c0; i++) o[(int64_t)i * es] = pin[(int64_t)(rel + i) * ss] ? 1 : 0;
-}
-
 // ----------------------------------------------------------------------------
 // S10 _combine_flags (flagging.py:784-816) + S11 _unaverage_freq (878-918)
 // ----------------------------------------------------------------------------

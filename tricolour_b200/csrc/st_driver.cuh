@@ -252,11 +252,6 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     bool need_cum = false;
     for (int k = 0; k < nwin; k++)
         if (windows[k] != 1 && windows[k] != 2 && windows[k] != 4 && windows[k] != 8) need_cum = true;
-    // prefix ring in shared memory (64 threads per block) when the widest window fits
-    const size_t ring_bytes = (size_t)maxw * 64 * sizeof(double);
-    const bool use_ring = need_cum && !s.fused1248 && ring_bytes + 1024 <= (size_t)c->smem_optin &&
-                          !getenv("TC_ST_NO_RING");
-    if (use_ring) need_cum = false;
     s.cum = nullptr;
     if (need_cum) TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad + 1) * ninner, &s.cum));
     s.pn = s.pn2 = nullptr;
@@ -265,13 +260,7 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
         TC_TRY(tc_alloc(c, (size_t)np * nchunks * (mpad > 0 ? mpad : 1) * ninner, &s.pn2));
     }
     tc_prof_begin(c, TCP_ST_SCAN);
-    if (use_ring) {
-        if (ring_bytes > 48 * 1024)
-            TC_CUDA(cudaFuncSetAttribute(k_st_scan_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-        TC_LAUNCH_NOSYNC(k_st_scan_ring, tc_blocks_for(nlines * nchunks, 64), 64, ring_bytes, c->stream, s);
-    } else {
-        TC_LAUNCH_NOSYNC(k_st_scan, tc_blocks_for(nlines * nchunks, 128), 128, 0, c->stream, s);
-    }
+    TC_LAUNCH_NOSYNC(k_st_scan, tc_blocks_for(nlines * nchunks, 128), 128, 0, c->stream, s);
     tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();

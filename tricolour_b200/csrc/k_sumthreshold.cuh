@@ -445,8 +445,8 @@ __device__ __forceinline__ void st_fused_1248(const float *__restrict__ d, u8 *_
     }
 }
 
-// Branch-free form of the single-sweep scan (same window lags, same per-window
-// arithmetic, so the flags are identical).  Differences from st_fused_1248:
+// Branch-free form of the single-sweep scan (same per-window arithmetic, so
+// the flags are identical).  Differences from st_fused_1248:
 //   * the line is cut into blocks of 8 steps; interior blocks (every window
 //     inside the line, every output inside the chunk) carry no predicates;
 //   * "x > limit" on a float32 sample is decided in float32 against the
@@ -498,6 +498,10 @@ __device__ __forceinline__ unsigned st2_step(St2Win &w, double *ring, int slot, 
     return ((w.h & MP) ? 1u : 0u) | ((w.h & (MP << 1)) ? 2u : 0u);
 }
 
+// Window k+1 trails window k by one step more than it strictly has to (sample
+// positions s, s-1, s-3, s-7; outputs at s-14), so that within a step no window
+// waits for another: the four float64 chains are independent.  The pos/neg
+// state of the samples in flight lives in 2-bit-per-sample shift registers.
 __device__ __forceinline__ void st_fused_1248_v2(const float *__restrict__ d, u8 *__restrict__ out, int m, int rel,
                                                  int nout, int64_t es, float thr, const double *tf,
                                                  const float *scale)
@@ -513,35 +517,33 @@ __device__ __forceinline__ void st_fused_1248_v2(const float *__restrict__ d, u8
     const int nj0 = m, nj1 = m - 1 > 0 ? m - 1 : 0, nj2 = m - 3 > 0 ? m - 3 : 0, nj3 = m - 7 > 0 ? m - 7 : 0;
     double h0[1] = {0.0}, h1[2] = {0.0, 0.0}, h2[4] = {0.0, 0.0, 0.0, 0.0}, h3[8];
     float xr[8];             // x[s - q] in xr[(s - q) & 7]
-    unsigned p0prev = 0u;    // pn_0(s - 1)
-    unsigned p1r[4];         // pn_1(j) in p1r[j & 3]
-    unsigned p2r[8];         // pn_2(j) in p2r[j & 7]
+    // state histories, newest sample in bits 1:0 (before this step's push):
+    unsigned p0h = 0u;       // pn_0(s - 1), pn_0(s - 2), ...
+    unsigned p1h = 0u;       // pn_1(s - 3), pn_1(s - 4), ...
+    unsigned p2h = 0u;       // pn_2(s - 7), pn_2(s - 8), ...
 #pragma unroll
-    for (int k = 0; k < 8; k++) { h3[k] = 0.0; xr[k] = 0.f; p2r[k] = 0u; }
-#pragma unroll
-    for (int k = 0; k < 4; k++) p1r[k] = 0u;
+    for (int k = 0; k < 8; k++) { h3[k] = 0.0; xr[k] = 0.f; }
     const float *pd = d;                              // sample s
-    u8 *po = out + (int64_t)(-11 - rel) * es;         // output of sample j = s - 11 (only dereferenced in range)
-    const int nsteps = m + 11;
-    // window starts at step s: j0 = s, j1 = s - 1, j2 = s - 4, j3 = s - 11
+    u8 *po = out + (int64_t)(-14 - rel) * es;         // output of sample j = s - 14 (only dereferenced in range)
+    const int nsteps = m + 14;
+    // window starts at step s: j0 = s, j1 = s - 2, j2 = s - 6, j3 = s - 14
     for (int s0 = 0; s0 < nsteps; s0 += 8) {
         // interior: all starts valid for the whole block, all 8 outputs inside the chunk
-        const bool interior = s0 >= 11 + rel && s0 + 7 < nj3 && s0 + 7 - 11 - rel < nout;
+        const bool interior = s0 >= 14 + rel && s0 + 7 < nj3 && s0 + 7 - 14 - rel < nout;
         if (interior) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const float xs = *pd;
                 pd += es;
                 xr[k] = xs;
-                const unsigned p0 = st2_step<1, true>(w0, h0, 0, xs, 0u, 0, 0);
-                const unsigned a1 = st2_step<2, true>(w1, h1, k & 1, xs, p0, 0, 0);
-                p1r[(k + 3) & 3] = p0prev | a1;
-                p0prev = p0;
-                const unsigned a2 = st2_step<4, true>(w2, h2, (k + 3) & 3, xr[(k + 7) & 7], p1r[(k + 3) & 3], 0, 0);
-                p2r[(k + 4) & 7] = p1r[k & 3] | a2;
-                const unsigned a3 = st2_step<8, true>(w3, h3, (k + 4) & 7, xr[(k + 4) & 7], p2r[(k + 4) & 7], 0, 0);
-                *po = (p2r[(k + 5) & 7] | a3) ? 1 : 0;
+                const unsigned a0 = st2_step<1, true>(w0, h0, 0, xs, 0u, 0, 0);
+                const unsigned a1 = st2_step<2, true>(w1, h1, (k + 1) & 1, xr[(k + 7) & 7], p0h & 3u, 0, 0);
+                const unsigned a2 = st2_step<4, true>(w2, h2, (k + 5) & 3, xr[(k + 5) & 7], p1h & 3u, 0, 0);
+                const unsigned a3 = st2_step<8, true>(w3, h3, (k + 1) & 7, xr[(k + 1) & 7], p2h & 3u, 0, 0);
+                *po = (((p2h >> 14) & 3u) | a3) ? 1 : 0;
                 po += es;
+                const unsigned n1 = ((p0h >> 2) & 3u) | a1, n2 = ((p1h >> 6) & 3u) | a2;
+                p0h = (p0h << 2) | a0; p1h = (p1h << 2) | n1; p2h = (p2h << 2) | n2;
             }
         } else {
 #pragma unroll
@@ -550,16 +552,15 @@ __device__ __forceinline__ void st_fused_1248_v2(const float *__restrict__ d, u8
                 const float xs = s < m ? *pd : 0.f;
                 pd += es;
                 xr[k] = xs;
-                const unsigned p0 = st2_step<1, false>(w0, h0, 0, xs, 0u, s, nj0);
-                const unsigned a1 = st2_step<2, false>(w1, h1, k & 1, xs, p0, s - 1, nj1);
-                p1r[(k + 3) & 3] = p0prev | a1;
-                p0prev = p0;
-                const unsigned a2 = st2_step<4, false>(w2, h2, (k + 3) & 3, xr[(k + 7) & 7], p1r[(k + 3) & 3], s - 4, nj2);
-                p2r[(k + 4) & 7] = p1r[k & 3] | a2;
-                const unsigned a3 = st2_step<8, false>(w3, h3, (k + 4) & 7, xr[(k + 4) & 7], p2r[(k + 4) & 7], s - 11, nj3);
-                const int o = s - 11 - rel;
-                if ((unsigned)o < (unsigned)nout && s - 11 < m) *po = (p2r[(k + 5) & 7] | a3) ? 1 : 0;
+                const unsigned a0 = st2_step<1, false>(w0, h0, 0, xs, 0u, s, nj0);
+                const unsigned a1 = st2_step<2, false>(w1, h1, (k + 1) & 1, xr[(k + 7) & 7], p0h & 3u, s - 2, nj1);
+                const unsigned a2 = st2_step<4, false>(w2, h2, (k + 5) & 3, xr[(k + 5) & 7], p1h & 3u, s - 6, nj2);
+                const unsigned a3 = st2_step<8, false>(w3, h3, (k + 1) & 7, xr[(k + 1) & 7], p2h & 3u, s - 14, nj3);
+                const int o = s - 14 - rel;
+                if ((unsigned)o < (unsigned)nout && s - 14 < m) *po = (((p2h >> 14) & 3u) | a3) ? 1 : 0;
                 po += es;
+                const unsigned n1 = ((p0h >> 2) & 3u) | a1, n2 = ((p1h >> 6) & 3u) | a2;
+                p0h = (p0h << 2) | a0; p1h = (p1h << 2) | n1; p2h = (p2h << 2) | n2;
             }
         }
     }

@@ -19,6 +19,8 @@ d = (torch.rand(P, T, F, device=dev) + 0.5).float()
 fl = (torch.rand(P, T, F, device=dev) < 0.3).to(torch.uint8)
 out = torch.empty_like(d)
 ctx = _cabi.get_context(0, _cabi.torch_stream_handle(0))
+if os.environ.get("TC_LIB"):
+    _cabi._set_library_for_testing(_cabi.load(os.environ["TC_LIB"]))
 lib = _cabi.load()
 radii = [(54, 43), (43, 34), (32, 25), (21, 17), (10, 8), (28, 277), (22, 221), (16, 166), (11, 110), (5, 55),
          (8, 43), (6, 34), (5, 25), (3, 17), (1, 8), (0, 43)]

@@ -129,28 +129,34 @@ k_uv_smooth(const float2 *__restrict__ avg, const double2 *__restrict__ tw, int 
 
 // absresidual = np.abs(vis - smooth) in float32.  numpy's complex64 absolute
 // on FMA hosts is max * sqrtf(fmaf(d, d, 1)), d = min / max.
-__global__ void __launch_bounds__(256)
-k_uv_absres(const float2 *__restrict__ vis, const float2 *__restrict__ smooth, int64_t total,
-            int T, int F, float *__restrict__ out)
+__device__ __forceinline__ float uv_abs_c64(float vx, float vy, float sx, float sy)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int64_t row = i / F;
-    int f = (int)(i - row * F);
-    int64_t cp = row / T;
-    float2 v = vis[i], s = smooth[cp * F + f];
-    float re = fabsf(__fadd_rn(v.x, -s.x)), im = fabsf(__fadd_rn(v.y, -s.y));
-    float r;
-    if (re != re || im != im) {
-        r = (isinf(re) || isinf(im)) ? INFINITY : NAN;
+    float re = fabsf(__fadd_rn(vx, -sx)), im = fabsf(__fadd_rn(vy, -sy));
+    if (re != re || im != im) return (isinf(re) || isinf(im)) ? INFINITY : NAN;
+    float mx = re > im ? re : im, mn = re > im ? im : re;
+    if (mx == 0.0f) return 0.0f;
+    if (isinf(mx)) return INFINITY;
+    float d = __fdiv_rn(mn, mx);
+    return mx * sqrtf(fmaf(d, d, 1.0f));
+}
+
+// grid: (ceil(F / 2 / 256), T, cp); two channels per thread, no index divisions
+__global__ void __launch_bounds__(256)
+k_uv_absres(const float2 *__restrict__ vis, const float2 *__restrict__ smooth, int T, int F,
+            float *__restrict__ out)
+{
+    const int f = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (f >= F) return;
+    const int64_t cp = blockIdx.z;
+    const int64_t row = (cp * T + blockIdx.y) * (int64_t)F;
+    const float2 *v = vis + row + f;
+    const float2 *s = smooth + cp * F + f;
+    if (f + 1 < F && (((uintptr_t)v | (uintptr_t)s) & 15) == 0 && (((uintptr_t)(out + row + f)) & 7) == 0) {
+        const float4 vv = *reinterpret_cast<const float4 *>(v), ss = *reinterpret_cast<const float4 *>(s);
+        *reinterpret_cast<float2 *>(out + row + f) =
+            make_float2(uv_abs_c64(vv.x, vv.y, ss.x, ss.y), uv_abs_c64(vv.z, vv.w, ss.z, ss.w));
     } else {
-        float mx = re > im ? re : im, mn = re > im ? im : re;
-        if (mx == 0.0f) r = 0.0f;
-        else if (isinf(mx)) r = INFINITY;
-        else {
-            float d = __fdiv_rn(mn, mx);
-            r = mx * sqrtf(fmaf(d, d, 1.0f));
-        }
+        out[row + f] = uv_abs_c64(v[0].x, v[0].y, s[0].x, s[0].y);
+        if (f + 1 < F) out[row + f + 1] = uv_abs_c64(v[1].x, v[1].y, s[1].x, s[1].y);
     }
-    out[i] = r;
 }

@@ -300,8 +300,8 @@ int tc_uvcontsub(tc_context *c, const void *vis, const uint8_t *flags, int64_t n
         TC_LAUNCH(k_uv_mean, dim3(tc_blocks_for(F, 256), (unsigned)ncp), 256, 0, c->stream, dvis, dout, (int)T,
                   (int)F, avg, unfl);
         TC_LAUNCH(k_uv_smooth, (unsigned)ncp, 256, 0, c->stream, avg, tw, (int)F, K, smooth);
-        TC_LAUNCH_NOSYNC(k_uv_absres, tc_blocks_for(total, 256), 256, 0, c->stream, dvis, smooth, total, (int)T,
-                         (int)F, absres);
+        TC_LAUNCH_NOSYNC(k_uv_absres, dim3(tc_blocks_for((F + 1) / 2, 256), (unsigned)T, (unsigned)ncp), 256, 0,
+                         c->stream, dvis, smooth, (int)T, (int)F, absres);
         tc_prof_end(c);
         c->launches += 3;
         ChunkSelectArgs s;

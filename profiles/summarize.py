@@ -19,7 +19,7 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "SM_A.TriageCompute.sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 
@@ -101,18 +101,22 @@ def stalls(rep, out):
 
 
 if __name__ == "__main__":
+    import os
     tot = launches()
     rows = raw(TAG + "_box_filter", "profiles/%s_box_filter_metrics.csv" % TAG)
-    raw(TAG + "_other", "profiles/%s_other_kernels_metrics.csv" % TAG)
     stalls(TAG + "_box_filter", "profiles/%s_box_filter_stalls.txt" % TAG)
-    stalls(TAG + "_other", "profiles/%s_other_kernels_stalls.txt" % TAG)
+    if os.path.exists("%s/%s_other.ncu-rep" % (SRC, TAG)):
+        raw(TAG + "_other", "profiles/%s_other_kernels_metrics.csv" % TAG)
+        stalls(TAG + "_other", "profiles/%s_other_kernels_stalls.txt" % TAG)
     # DRAM traffic per launch of the dominant kernel family, for bench.py's roofline.traffic
     h = rows[0]
     rd, wr, nm = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
     unit = rows[1][rd]
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
-    per = [(float(r[rd]) + float(r[wr])) * scale for r in rows[2:] if "k_box_filter" in r[nm]]
-    json.dump({"kernel": "box_filter", "dram_bytes_per_launch": sum(per) / len(per), "launches_sampled": len(per),
+    # the dominant family: the lane-per-chain kernel of the second filtered axis (k_box4, big launches only)
+    per = [(float(r[rd]) + float(r[wr])) * scale for r in rows[2:]
+           if "k_box4" in r[nm] and (float(r[rd]) + float(r[wr])) * scale > 1e8]
+    json.dump({"kernel": "box_filter (k_box4)", "dram_bytes_per_launch": sum(per) / len(per), "launches_sampled": len(per),
                "source": "ncu --set full, %s_box_filter.ncu-rep (16 baselines x 4 corr x 512 x 4096 block)" % TAG},
               open("profiles/%s_traffic.json" % TAG, "w"), indent=1)
     print("total ms in launch list:", tot)

@@ -442,7 +442,7 @@ def test_sum_threshold_flagger(backend):
 
 def test_sum_threshold_flagger_aligned(backend):
     """shapes with T % 16 == 0 and F % 16 == 0 take the vectorised / thread-per-line kernels"""
-    shape = (2, 2, 64, 256) if big(backend) else (1, 1, 32, 64)
+    shape = (2, 2, 64, 256) if big(backend) else (1, 2, 32, 64)
     vis, flags = common.make_windows(*shape, seed=27)
     cases = [dict(num_major_iterations=1, background_iterations=2),
              dict(num_major_iterations=1, background_iterations=1, spike_width_time=2, spike_width_freq=4.0,

@@ -67,6 +67,46 @@ k_prep_c64_v4(const float4 *__restrict__ vis, const unsigned *__restrict__ flags
     out_flags[o] = of;
 }
 
+// The same with both layouts written at once: a block owns a tile of 32 dumps x
+// 32 channels, writes it to (cp, T, F) directly and to (cp, F, T) through a
+// shared-memory transpose.  grid (F / 32, T / 32, cp), 256 threads.
+__global__ void __launch_bounds__(256)
+k_prep_c64_tile(const float4 *__restrict__ vis, const unsigned *__restrict__ flags, int T, int F,
+                float4 *__restrict__ d_TF, unsigned *__restrict__ f_TF, float4 *__restrict__ d_FT,
+                unsigned *__restrict__ f_FT)
+{
+    __shared__ float td[32][33];
+    __shared__ u8 tf[32][36];
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const int64_t cp = blockIdx.z;
+    const int t0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
+    {
+        const int64_t idx = ((cp * T + t0 + ty) * (int64_t)F + f0 + tx * 4) >> 2;   // in units of 4 samples
+        const float4 a = vis[2 * idx], b = vis[2 * idx + 1];
+        const unsigned f = flags[idx];
+        float amp[4] = {tc_abs_c64(a.x, a.y), tc_abs_c64(a.z, a.w), tc_abs_c64(b.x, b.y), tc_abs_c64(b.z, b.w)};
+        unsigned of = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool bad = ((f >> (8 * k)) & 0xffu) || amp[k] != amp[k];
+            amp[k] = bad ? 0.0f : __fdiv_rn(__fadd_rn(0.0f, amp[k]), 1.0f);
+            of |= bad ? (1u << (8 * k)) : 0u;
+            td[tx * 4 + k][ty] = amp[k];
+            tf[tx * 4 + k][ty] = bad ? 1 : 0;
+        }
+        d_TF[idx] = make_float4(amp[0], amp[1], amp[2], amp[3]);
+        f_TF[idx] = of;
+    }
+    __syncthreads();
+    {
+        // row ty of the transposed tile = channel f0 + ty, dumps t0 + 4 tx .. + 3
+        const int64_t idx = ((cp * F + f0 + ty) * (int64_t)T + t0 + tx * 4) >> 2;
+        d_FT[idx] = make_float4(td[ty][tx * 4], td[ty][tx * 4 + 1], td[ty][tx * 4 + 2], td[ty][tx * 4 + 3]);
+        f_FT[idx] = (unsigned)tf[ty][tx * 4] | ((unsigned)tf[ty][tx * 4 + 1] << 8) |
+                    ((unsigned)tf[ty][tx * 4 + 2] << 16) | ((unsigned)tf[ty][tx * 4 + 3] << 24);
+    }
+}
+
 // flags[(cp,t,f)] |= spec[(cp,f)]   (flagging.py:954)
 __global__ void __launch_bounds__(256)
 k_or_spec(u8 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total, int T, int Fa)
@@ -190,7 +230,7 @@ k_interp_nans_rows(const float *__restrict__ bg, const float *__restrict__ minue
         const bool valid = i < n && !(x[i] != x[i]);
         const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
         const unsigned mm = m >> lane;
-        if (i < n) r[i] = mm ? i + __ffs((int)mm) - 1 : carry;
+        if (i < n && !valid) r[i] = mm ? i + __ffs((int)mm) - 1 : carry;   // only NaN samples look it up
         if (m) carry = t * 32 + __ffs((int)m) - 1;
         nnan += (i < n && !valid) ? 1 : 0;
     }

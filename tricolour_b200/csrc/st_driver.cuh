@@ -339,18 +339,29 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_TRY(tc_alloc(c, N, &fl_TF)); TC_TRY(tc_alloc(c, N, &fl_FT));
     // S1 _average_freq
     tc_prof_begin(c, TCP_PREP);
-    if (avg == 1 && vis_kind == TC_VIS_COMPLEX64 && (N & 3) == 0 && ((uintptr_t)vis & 15) == 0 &&
-        ((uintptr_t)in_flags & 3) == 0)
-        TC_LAUNCH_NOSYNC(k_prep_c64_v4, tc_blocks_for(N / 4, 256), 256, 0, c->stream, (const float4 *)vis,
-                         (const unsigned *)in_flags, N / 4, (float4 *)data_TF, (unsigned *)fl_TF);
-    else
-        TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
-                         data_TF, fl_TF);
-    tc_prof_end(c);
-    c->launches++;
-    TC_KERNEL_CHECK();
-    TC_TRY(launch_transpose<float>(c, data_TF, data_FT, np, T, Fa));
-    TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+    const bool vec_ok = avg == 1 && vis_kind == TC_VIS_COMPLEX64 && (N & 3) == 0 && ((uintptr_t)vis & 15) == 0 &&
+                        ((uintptr_t)in_flags & 3) == 0;
+    if (vec_ok && (T & 31) == 0 && (F & 31) == 0 && np <= 65535 && T / 32 <= 65535) {
+        // amplitudes and flags in both layouts from one kernel
+        TC_LAUNCH(k_prep_c64_tile, dim3((unsigned)(F / 32), (unsigned)(T / 32), (unsigned)np), 256, 0, c->stream,
+                  (const float4 *)vis, (const unsigned *)in_flags, T, F, (float4 *)data_TF, (unsigned *)fl_TF,
+                  (float4 *)data_FT, (unsigned *)fl_FT);
+        tc_prof_end(c);
+        c->launches++;
+        TC_KERNEL_CHECK();
+    } else {
+        if (vec_ok)
+            TC_LAUNCH_NOSYNC(k_prep_c64_v4, tc_blocks_for(N / 4, 256), 256, 0, c->stream, (const float4 *)vis,
+                             (const unsigned *)in_flags, N / 4, (float4 *)data_TF, (unsigned *)fl_TF);
+        else
+            TC_LAUNCH_NOSYNC(k_prep, tc_blocks_for(N, 256), 256, 0, c->stream, vis, vis_kind, in_flags, N, F, Fa, avg,
+                             data_TF, fl_TF);
+        tc_prof_end(c);
+        c->launches++;
+        TC_KERNEL_CHECK();
+        TC_TRY(launch_transpose<float>(c, data_TF, data_FT, np, T, Fa));
+        TC_TRY(launch_transpose<u8>(c, fl_TF, fl_FT, np, T, Fa));
+    }
 
     // S2 _time_median -> (np, Fa)
     float *spec_data, *spec_bg;

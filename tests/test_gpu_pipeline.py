@@ -180,3 +180,24 @@ def test_full_block_properties(cuda_lib):
     assert np.array_equal(a[5:6, 1:2], d)
     st = tb.window_stats(a, ubl, common.channels(F)[0], ["m%03d" % i for i in range(64)], 0, "f", 0)
     assert int(st._counts_per_field["f"]) == int(a.sum())
+
+
+@pytest.mark.gpu
+def test_pipelined_executor_matches_block_by_block(cuda_lib):
+    """apply_strategies_pipelined (transfers overlapped with flagging) returns, block
+    for block, what apply_strategies returns"""
+    import tricolour_b200 as tb
+    nbl, T, F = 3, 32, 128
+    ubl = common.baselines(8)[:nbl].copy()
+    ants = common.antenna_layout(8)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    ex = tb.StrategyExecutor(ants, ubl, cf, cw, masks, common.default_strategies())
+    blocks = [common.make_windows(nbl, 2, T, F, seed=90 + k, ubl=ubl) for k in range(4)]
+    want = [ex.apply_strategies(f, v) for v, f in blocks]
+    got = list(ex.apply_strategies_pipelined([(f, v) for v, f in blocks]))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype and g.shape == w.shape
+        assert np.array_equal(g, w)
+    assert list(ex.apply_strategies_pipelined([])) == []

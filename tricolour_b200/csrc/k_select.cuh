@@ -693,7 +693,7 @@ __device__ __forceinline__ uint32_t brk_hash(uint32_t x)
     return x;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo)
 {
     __shared__ uint32_t keys[TC_BRK_SAMPLES];
@@ -706,7 +706,7 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     __syncthreads();
     const bool exact = len <= TC_BRK_SAMPLES;
     int nv = 0;
-    for (int j = tid; j < TC_BRK_SAMPLES; j += 256) {
+    for (int j = tid; j < TC_BRK_SAMPLES; j += (int)blockDim.x) {
         uint32_t k = 0xffffffffu;
         int64_t pos = -1;
         if (exact) { if (j < len) pos = lo + j; }
@@ -727,7 +727,7 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     // bitonic sort of 2048 keys (invalid keys = 0xffffffff sink to the end)
     for (int size = 2; size <= TC_BRK_SAMPLES; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < TC_BRK_SAMPLES / 2; t += 256) {
+            for (int t = tid; t < TC_BRK_SAMPLES / 2; t += (int)blockDim.x) {
                 int i = 2 * t - (t & (stride - 1));
                 int j = i + stride;
                 bool up = (i & size) == 0;
@@ -975,7 +975,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         if (b.medians) b.medians += r0;
         if (b.uv_unflagged) b.uv_unflagged += r0;
         b.medbuf += r0;
-        TC_LAUNCH(k_brk_sample, nr, 256, 0, c->stream, b, st + r0, todo + r0);
+        TC_LAUNCH(k_brk_sample, nr, 1024, 0, c->stream, b, st + r0, todo + r0);
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + TC_BRK_SLICE - 1) / TC_BRK_SLICE);

@@ -84,6 +84,95 @@ class StrategyExecutor(object):
             out = flags.view(torch.uint8).cpu().numpy()
         return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
 
+    def apply_strategies_pipelined(self, blocks, device=None, depth=2):
+        """Flags a sequence of host blocks, overlapping transfers with flagging.
+
+        ``blocks`` yields ``(flag_windows, vis_windows)`` numpy pairs (page-locked
+        buffers make the uploads asynchronous); the flags of every block are
+        yielded in order as numpy arrays.  The upload of block i+1 runs on a copy
+        stream while block i is being flagged, the download of block i on a third
+        stream while block i+1 is being flagged -- the dask scheduler of the
+        reference overlaps its I/O with flagging the same way (app.py:266-271).
+        Device and page-locked staging buffers for ``depth`` + 1 blocks are kept
+        on the executor and reused.
+        """
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("tricolour_b200: no CUDA device available; there is no CPU fallback")
+        dev = torch.device("cuda", _cabi.default_device() if device is None else int(device))
+        nslots = max(1, int(depth)) + 1
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            pipe = self.__dict__.setdefault("_pipe", {})
+            if pipe.get("dev") != dev or pipe.get("nslots") != nslots:
+                pipe.clear()
+                pipe.update(dev=dev, nslots=nslots, up=torch.cuda.Stream(device=dev),
+                            down=torch.cuda.Stream(device=dev), shape=None)
+            up_s, down_s = pipe["up"], pipe["down"]
+
+            def buffers(shape):
+                if pipe["shape"] != tuple(shape):
+                    pipe["shape"] = tuple(shape)
+                    pipe["f"] = [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(nslots)]
+                    pipe["v"] = [torch.empty(shape, dtype=torch.complex64, device=dev) for _ in range(nslots)]
+                    pipe["h"] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True) for _ in range(nslots)]
+                    pipe["free"] = [None] * nslots      # event: the slot's device buffers may be overwritten
+                return pipe
+
+            def upload(pair, k):
+                f_np = np.ascontiguousarray(pair[0])
+                f8 = f_np.view(np.uint8) if f_np.dtype.itemsize == 1 else (f_np != 0).view(np.uint8)
+                v_np = np.ascontiguousarray(pair[1], dtype=np.complex64)
+                b = buffers(f8.shape)
+                slot = k % nslots
+                with torch.cuda.stream(up_s):
+                    if b["free"][slot] is not None:
+                        up_s.wait_event(b["free"][slot])
+                    b["f"][slot].copy_(torch.from_numpy(f8), non_blocking=True)
+                    b["v"][slot].copy_(torch.from_numpy(v_np), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(up_s)
+                return slot, ev, f_np.dtype
+
+            def finish(item):
+                slot, ev, fdt = item
+                ev.synchronize()
+                out = pipe["h"][slot].numpy().copy()     # the page-locked buffer is reused
+                return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
+
+            it = iter(blocks)
+            pending = []          # downloads in flight
+            k = 0
+            try:
+                nxt = upload(next(it), k)
+            except StopIteration:
+                return
+            while nxt is not None:
+                cur = nxt
+                k += 1
+                # a slot's page-locked output must have been consumed before its reuse
+                while len(pending) >= nslots - 1:
+                    yield finish(pending.pop(0))
+                try:
+                    nxt = upload(next(it), k)      # queued before this block's kernels: overlaps them
+                except StopIteration:
+                    nxt = None
+                slot, ev_up, fdt = cur
+                main.wait_event(ev_up)
+                res = self._run(pipe["f"][slot].view(torch.bool), pipe["v"][slot])
+                ev_done = torch.cuda.Event()
+                ev_done.record(main)
+                pipe["free"][slot] = ev_done
+                with torch.cuda.stream(down_s):
+                    down_s.wait_event(ev_done)
+                    pipe["h"][slot].copy_(res.view(torch.uint8), non_blocking=True)
+                    ev_out = torch.cuda.Event()
+                    ev_out.record(down_s)
+                    res.record_stream(down_s)
+                pending.append((slot, ev_out, fdt))
+            while pending:
+                yield finish(pending.pop(0))
+
     def _run(self, flag_windows, vis_windows):
         original = flag_windows.clone()
         ubl = np.asarray(self.ubl)

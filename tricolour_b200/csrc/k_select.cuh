@@ -298,6 +298,7 @@ struct ChunkSelectArgs {
     const int *uv_unflagged;  // [nranges] number of unflagged samples (0 -> plane skipped)
     const unsigned *todo;     // optional [nranges]: the sliced radix kernels only touch ranges with todo != 0
     double *medbuf;           // [nranges] where the sliced paths leave the median for k_sel_update
+    float brk_k;              // half width of the sample bracket in units of sqrt(sample size)
 };
 
 #define TC_SEL_BINS 2048
@@ -754,7 +755,7 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
             b.n_valid = (uint32_t)sv;
         } else if (sv >= 64) {
             int mid = sv >> 1;
-            int delta = (int)(2.5f * sqrtf((float)sv)) + 4;
+            int delta = (int)(a.brk_k * sqrtf((float)sv)) + 4;
             b.lo = mid - delta >= 0 ? keys[mid - delta] : 0u;
             b.hi = mid + delta < sv ? keys[mid + delta] : 0xfffffffeu;
         }
@@ -962,6 +963,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     TC_TRY(tc_alloc(c, (size_t)nranges, &todo));
     if (!a.medbuf) TC_TRY(tc_alloc(c, (size_t)nranges, &a.medbuf));
     const bool small = max_range <= TC_BRK_SAMPLES;
+    a.brk_k = getenv("TC_BRK_K") ? (float)atof(getenv("TC_BRK_K")) : 1.75f;   // +-3.5 sigma of the sample rank of the median
     const int64_t cap = small ? 1 : max_range / 4 + 4096;
     uint32_t *cbuf = nullptr;
     if (!small) TC_TRY(tc_alloc(c, (size_t)nranges * cap, &cbuf));

@@ -883,3 +883,32 @@ k_norm_flags(const u8 *__restrict__ in, u8 *__restrict__ out, int64_t n)
     if (i >= n) return;
     out[i] = in[i] ? 1 : 0;
 }
+
+// the same, 16 flags per thread (both pointers 16-byte aligned, n16 = n / 16)
+__global__ void __launch_bounds__(256)
+k_norm_flags_v16(const uint4 *__restrict__ in, uint4 *__restrict__ out, int64_t n16)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    uint4 v = in[i];
+    unsigned *w = reinterpret_cast<unsigned *>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // every non-zero byte -> 1: fold the bits of each byte into its lowest bit
+        unsigned x = w[q];
+        x |= x >> 4; x |= x >> 2; x |= x >> 1;
+        w[q] = x & 0x01010101u;
+    }
+    out[i] = v;
+}
+
+static int launch_norm_flags(tc_context *c, const u8 *in, u8 *out, int64_t n)
+{
+    if (n <= 0) return TC_OK;
+    const int64_t n16 = ((((uintptr_t)in | (uintptr_t)out) & 15) == 0) ? n / 16 : 0;
+    if (n16) TC_LAUNCH_NOSYNC(k_norm_flags_v16, tc_blocks_for(n16, 256), 256, 0, c->stream, (const uint4 *)in, (uint4 *)out, n16);
+    if (n - 16 * n16)
+        TC_LAUNCH_NOSYNC(k_norm_flags, tc_blocks_for(n - 16 * n16, 256), 256, 0, c->stream, in + 16 * n16, out + 16 * n16,
+                         n - 16 * n16);
+    return TC_OK;
+}

@@ -249,7 +249,7 @@ int tc_sum_threshold(tc_context *c, const tc_st_params *p, const void *vis, int 
         TC_TRY(tc_stage_in(c, flags + p0 * T * F, (size_t)n, space, &dfl));
         u8 *iter_flags;
         TC_TRY(tc_alloc(c, (size_t)n, &iter_flags));
-        TC_LAUNCH_NOSYNC(k_norm_flags, tc_blocks_for(n, 256), 256, 0, c->stream, dfl, iter_flags, n);
+        TC_TRY(launch_norm_flags(c, dfl, iter_flags, n));
         c->launches++;
         TC_KERNEL_CHECK();
         for (int it = 0; it < p->num_major_iterations; it++)
@@ -276,7 +276,7 @@ int tc_uvcontsub(tc_context *c, const void *vis, const uint8_t *flags, int64_t n
     TC_TRY(tc_stage_out_begin(c, out, (size_t)total, space, &dout));
     if (total == 0) return tc_stage_out_end(c, out, dout, 0, space);
     // result_flags = flags.copy() (boolean semantics)
-    TC_LAUNCH_NOSYNC(k_norm_flags, tc_blocks_for(total, 256), 256, 0, c->stream, dfl, dout, total);
+    TC_TRY(launch_norm_flags(c, dfl, dout, total));
     c->launches++;
     int K = taylor_degrees < (int)F ? taylor_degrees : (int)F;
     TC_REQUIRE(K <= TC_UV_MAXK, "taylor_degrees above %d is not supported", TC_UV_MAXK);
@@ -559,7 +559,7 @@ static int stage_planes(tc_context *c, const float *data, const u8 *flags, int64
         TC_TRY(tc_stage_in(c, flags, (size_t)n, space, &raw));
         TC_TRY(tc_alloc(c, (size_t)n, &norm));
         if (n) {
-            TC_LAUNCH_NOSYNC(k_norm_flags, tc_blocks_for(n, 256), 256, 0, c->stream, raw, norm, n);
+            TC_TRY(launch_norm_flags(c, raw, norm, n));
             c->launches++;
         }
         s->f_TF = norm;

@@ -764,16 +764,111 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     }
 }
 
+// radix select of the wanted rank inside the compact buffer.  Runs as the tail of
+// the LAST collecting block of a range (every thread of the block calls it);
+// the buffer and the counters were written by other blocks, so they are read
+// past L1.
+__device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const BrkState *st, const uint32_t *cbuf,
+                                                int64_t cap, unsigned *todo, int range, uint32_t *hist,
+                                                uint32_t *s_wsum, uint32_t *s_scal)
+{
+    uint32_t &s_prefix = s_scal[0], &s_remaining = s_scal[1], &s_best = s_scal[2];
+    const int tid = threadIdx.x, nt = blockDim.x;   // 1024 threads
+    BrkState b;
+    b.lo = 0; b.hi = 0; b.done = 0; b.pad0 = b.pad1 = 0;
+    b.n_valid = __ldcg(&st[range].n_valid);
+    b.n_below = __ldcg(&st[range].n_below);
+    b.n_in = __ldcg(&st[range].n_in);
+    if (b.n_valid == 0) {
+        if (tid == 0) { a.medbuf[range] = NAN; if (a.medians) a.medians[range] = NAN; }
+        return;
+    }
+    const uint32_t kth = b.n_valid >> 1;
+    const bool even = (b.n_valid & 1u) == 0;
+    // the wanted rank (and, for even counts, a lower neighbour) must lie inside the buffer
+    if ((int64_t)b.n_in > cap || kth < b.n_below || kth >= b.n_below + b.n_in ||
+        (even && kth == b.n_below && b.n_below > 0)) {
+        if (tid == 0) todo[range] = 1;
+        return;
+    }
+    const uint32_t *keys = cbuf + (size_t)range * cap;
+    const uint32_t n = b.n_in;
+    uint32_t prefix = 0, himask = 0, remaining = kth - b.n_below;
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const uint32_t dmask = pass == 2 ? 1023u : 2047u;
+        for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += nt) {
+            uint32_t k = __ldcg(keys + i);
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
+        }
+        __syncthreads();
+        {
+            // parallel search of the digit: thread t owns bins [2t, 2t+2)
+            const int per = TC_SEL_BINS / 1024;
+            uint32_t loc[TC_SEL_BINS / 1024];
+            uint32_t sum = 0;
+            for (int q = 0; q < per; q++) { loc[q] = hist[tid * per + q]; sum += loc[q]; }
+            // inclusive scan of `sum` over the 1024 threads
+            uint32_t inc = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+                if ((tid & 31) >= o) inc += v;
+            }
+            if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < (tid >> 5); w++) woff += s_wsum[w];
+            const uint32_t excl = woff + inc - sum;
+            if (remaining >= excl && remaining < excl + sum) {
+                uint32_t acc = excl, digit = tid * per;
+                for (int q = 0; q < per; q++) {
+                    if (remaining < acc + loc[q]) { digit = tid * per + q; break; }
+                    acc += loc[q];
+                }
+                s_remaining = remaining - acc;
+                s_prefix = prefix | (digit << shift);
+            }
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        himask |= dmask << shift;
+        __syncthreads();
+    }
+    float upper = key2f(prefix), lower = upper;
+    if (even && remaining == 0) {
+        if (tid == 0) s_best = 0;
+        __syncthreads();
+        uint32_t best = 0;
+        for (uint32_t i = tid; i < n; i += nt) {
+            uint32_t k = __ldcg(keys + i);
+            if (k < prefix && k > best) best = k;
+        }
+        best = warp_max_u(best);
+        if ((tid & 31) == 0 && best) atomicMax(&s_best, best);
+        __syncthreads();
+        lower = key2f(s_best);
+    }
+    if (tid == 0) {
+        double med = median_from_pair(lower, upper, (int)b.n_valid);
+        a.medbuf[range] = med;
+        if (a.medians) a.medians[range] = med;
+    }
+}
+
 // sweep: count valid / below-bracket keys, copy in-bracket keys to the compact
 // buffer.  In-bracket keys are first gathered in shared memory (one shared
 // atomic per warp and iteration), then the block reserves its share of the
 // range's buffer with ONE global atomic and copies coalesced.
 #define TC_BRK_STAGE 8192
 __global__ void __launch_bounds__(1024)
-k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap)
+k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap,
+              unsigned *__restrict__ todo)
 {
     __shared__ uint32_t stage[TC_BRK_STAGE];
-    __shared__ uint32_t s_valid, s_below, s_in, s_base;
+    __shared__ uint32_t s_valid, s_below, s_in, s_base, s_last;
     const int range = blockIdx.y;
     if (st[range].done) return;
     const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_BRK_SLICE;
@@ -861,96 +956,18 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     const uint32_t base = s_base;
     for (uint32_t q = tid; q < cnt; q += nt)
         if ((int64_t)(base + q) < cap) out[base + q] = stage[q];
-}
-
-// radix select of the wanted rank inside the compact buffer
-__global__ void __launch_bounds__(512)
-k_brk_select(ChunkSelectArgs a, const BrkState *__restrict__ st, const uint32_t *__restrict__ cbuf, int64_t cap,
-             unsigned *__restrict__ todo)
-{
-    __shared__ uint32_t hist[TC_SEL_BINS];
-    __shared__ uint32_t s_prefix, s_remaining, s_best;
-    __shared__ uint32_t s_wsum[16];
-    const int range = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;  // launched with 512 threads
-    const BrkState b = st[range];
-    if (b.done) return;
-    if (b.n_valid == 0) {
-        if (tid == 0) { a.medbuf[range] = NAN; if (a.medians) a.medians[range] = NAN; }
-        return;
-    }
-    const uint32_t kth = b.n_valid >> 1;
-    const bool even = (b.n_valid & 1u) == 0;
-    // the wanted rank (and, for even counts, a lower neighbour) must lie inside the buffer
-    if ((int64_t)b.n_in > cap || kth < b.n_below || kth >= b.n_below + b.n_in ||
-        (even && kth == b.n_below && b.n_below > 0)) {
-        if (tid == 0) todo[range] = 1;
-        return;
-    }
-    const uint32_t *keys = cbuf + (size_t)range * cap;
-    const uint32_t n = b.n_in;
-    uint32_t prefix = 0, himask = 0, remaining = kth - b.n_below;
-    for (int pass = 0; pass < 3; pass++) {
-        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-        const uint32_t dmask = pass == 2 ? 1023u : 2047u;
-        for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += nt) {
-            uint32_t k = keys[i];
-            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
-        }
-        __syncthreads();
-        {
-            // parallel search of the digit: thread t owns bins [4t, 4t+4)
-            const int per = TC_SEL_BINS / 512;
-            uint32_t loc[TC_SEL_BINS / 512];
-            uint32_t sum = 0;
-            for (int q = 0; q < per; q++) { loc[q] = hist[tid * per + q]; sum += loc[q]; }
-            // inclusive scan of `sum` over the 512 threads
-            uint32_t inc = sum;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
-                if ((tid & 31) >= o) inc += v;
-            }
-            if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
-            __syncthreads();
-            uint32_t woff = 0;
-            for (int w = 0; w < (tid >> 5); w++) woff += s_wsum[w];
-            const uint32_t excl = woff + inc - sum;
-            if (remaining >= excl && remaining < excl + sum) {
-                uint32_t acc = excl, digit = tid * per;
-                for (int q = 0; q < per; q++) {
-                    if (remaining < acc + loc[q]) { digit = tid * per + q; break; }
-                    acc += loc[q];
-                }
-                s_remaining = remaining - acc;
-                s_prefix = prefix | (digit << shift);
-            }
-        }
-        __syncthreads();
-        prefix = s_prefix;
-        remaining = s_remaining;
-        himask |= dmask << shift;
-        __syncthreads();
-    }
-    float upper = key2f(prefix), lower = upper;
-    if (even && remaining == 0) {
-        if (tid == 0) s_best = 0;
-        __syncthreads();
-        uint32_t best = 0;
-        for (uint32_t i = tid; i < n; i += nt) {
-            uint32_t k = keys[i];
-            if (k < prefix && k > best) best = k;
-        }
-        best = warp_max_u(best);
-        if ((tid & 31) == 0 && best) atomicMax(&s_best, best);
-        __syncthreads();
-        lower = key2f(s_best);
-    }
+    // the block that finishes a range last selects inside the range's compact buffer
+    __threadfence();
+    __syncthreads();
     if (tid == 0) {
-        double med = median_from_pair(lower, upper, (int)b.n_valid);
-        a.medbuf[range] = med;
-        if (a.medians) a.medians[range] = med;
+        const int64_t len = a.range_hi[range] - a.range_lo[range];
+        const unsigned nactive = (unsigned)((len + TC_BRK_SLICE - 1) / TC_BRK_SLICE);
+        s_last = atomicAdd(&st[range].pad0, 1u) == nactive - 1 ? 1u : 0u;
     }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    brk_select_tail(a, st, cbuf, cap, todo, range, stage, stage + TC_SEL_BINS, stage + TC_SEL_BINS + 64);
 }
 
 static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int64_t nranges, int64_t max_range)
@@ -981,9 +998,8 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + TC_BRK_SLICE - 1) / TC_BRK_SLICE);
-            TC_LAUNCH(k_brk_collect, dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap);
-            TC_LAUNCH(k_brk_select, nr, 512, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap, todo + r0);
-            c->launches += 2;
+            TC_LAUNCH(k_brk_collect, dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap, todo + r0);
+            c->launches++;
         }
     }
     tc_prof_end(c);

@@ -138,6 +138,8 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __double2float_rn(double a) { return (float)a; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
+static inline void __threadfence() {}
 static inline float fminf_emu(float a, float b) { return a < b ? a : b; }
 
 #define TC_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -67,6 +67,11 @@ int tc_profile_read(tc_context *ctx, int id, double *total_ms, long long *launch
 size_t tc_workspace_peak(tc_context *ctx);
 int tc_alloc_pinned(size_t nbytes, void **out);
 int tc_free_pinned(void *ptr);
+/* asynchronous copy on the context's stream: kind 0 = host -> device, 1 = device -> host.
+ * With page-locked host memory the call returns at once; it is what the pipelined
+ * executor (tricolour_b200/strategy.py) stages blocks with -- the reference moves its
+ * blocks through dask (apps/tricolour/app.py:451-467). */
+int tc_memcpy_async(tc_context *ctx, void *dst, const void *src, size_t nbytes, int kind);
 /* 1 when the library was built with the CPU SIMT emulator (tests only) */
 int tc_is_emulated(void);
 

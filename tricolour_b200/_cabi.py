@@ -71,6 +71,7 @@ _SIGNATURES = {
     "tc_profile_read": (_int, [_vp, _int, ctypes.POINTER(_dbl), ctypes.POINTER(ctypes.c_longlong)]),
     "tc_alloc_pinned": (_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "tc_free_pinned": (_int, [_vp]),
+    "tc_memcpy_async": (_int, [_vp, _vp, _vp, ctypes.c_size_t, _int]),
     "tc_is_emulated": (_int, []),
     "tc_flag_nans_zeros": (_int, [_vp, _vp, _vp, _vp, _i64, _int]),
     "tc_flag_autos": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _int]),

@@ -112,6 +112,16 @@ int tc_free_pinned(void *p)
     TC_CUDA(cudaFreeHost(p));
     return TC_OK;
 }
+int tc_memcpy_async(tc_context *c, void *dst, const void *src, size_t nbytes, int kind)
+{
+    if (!c) return tc_fail(TC_ERR_VALUE, "null context");
+    TC_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (host to device) or 1 (device to host)");
+    TC_CUDA(cudaSetDevice(c->device));
+    if (nbytes)
+        TC_CUDA(cudaMemcpyAsync(dst, src, nbytes, kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                c->stream));
+    return TC_OK;
+}
 
 static int tc_begin(tc_context *c)
 {

@@ -119,20 +119,25 @@ class StrategyExecutor(object):
                     pipe["free"] = [None] * nslots      # event: the slot's device buffers may be overwritten
                 return pipe
 
+            lib = _cabi.load()
+            up_ctx = _cabi.get_context(dev.index, int(up_s.cuda_stream))
+            down_ctx = _cabi.get_context(dev.index, int(down_s.cuda_stream))
+
             def upload(pair, k):
                 f_np = np.ascontiguousarray(pair[0])
                 f8 = f_np.view(np.uint8) if f_np.dtype.itemsize == 1 else (f_np != 0).view(np.uint8)
                 v_np = np.ascontiguousarray(pair[1], dtype=np.complex64)
                 b = buffers(f8.shape)
                 slot = k % nslots
-                with torch.cuda.stream(up_s):
-                    if b["free"][slot] is not None:
-                        up_s.wait_event(b["free"][slot])
-                    b["f"][slot].copy_(torch.from_numpy(f8), non_blocking=True)
-                    b["v"][slot].copy_(torch.from_numpy(v_np), non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(up_s)
-                return slot, ev, f_np.dtype
+                if b["free"][slot] is not None:
+                    up_s.wait_event(b["free"][slot])
+                # raw asynchronous copies on the upload stream: with page-locked sources the host
+                # does not wait (torch would treat foreign page-locked memory as pageable)
+                check(lib.tc_memcpy_async(up_ctx.handle, ptr(b["f"][slot]), ptr(f8), int(f8.nbytes), 0))
+                check(lib.tc_memcpy_async(up_ctx.handle, ptr(b["v"][slot]), ptr(v_np), int(v_np.nbytes), 0))
+                ev = torch.cuda.Event()
+                ev.record(up_s)
+                return slot, ev, f_np.dtype, (f8, v_np)      # keep the sources alive until the copy ran
 
             def finish(item):
                 slot, ev, fdt = item
@@ -140,8 +145,11 @@ class StrategyExecutor(object):
                 out = pipe["h"][slot].numpy().copy()     # the page-locked buffer is reused
                 return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
 
+            from concurrent.futures import ThreadPoolExecutor
+            copier = pipe.setdefault("copier", ThreadPoolExecutor(max_workers=1))
+
             it = iter(blocks)
-            pending = []          # downloads in flight
+            pending = []          # futures of downloads in flight
             k = 0
             try:
                 nxt = upload(next(it), k)
@@ -152,26 +160,27 @@ class StrategyExecutor(object):
                 k += 1
                 # a slot's page-locked output must have been consumed before its reuse
                 while len(pending) >= nslots - 1:
-                    yield finish(pending.pop(0))
+                    yield pending.pop(0).result()
                 try:
                     nxt = upload(next(it), k)      # queued before this block's kernels: overlaps them
                 except StopIteration:
                     nxt = None
-                slot, ev_up, fdt = cur
+                slot, ev_up, fdt, _src = cur
                 main.wait_event(ev_up)
                 res = self._run(pipe["f"][slot].view(torch.bool), pipe["v"][slot])
                 ev_done = torch.cuda.Event()
                 ev_done.record(main)
                 pipe["free"][slot] = ev_done
-                with torch.cuda.stream(down_s):
-                    down_s.wait_event(ev_done)
-                    pipe["h"][slot].copy_(res.view(torch.uint8), non_blocking=True)
-                    ev_out = torch.cuda.Event()
-                    ev_out.record(down_s)
-                    res.record_stream(down_s)
-                pending.append((slot, ev_out, fdt))
+                down_s.wait_event(ev_done)
+                r8 = res.view(torch.uint8)
+                check(lib.tc_memcpy_async(down_ctx.handle, _cabi._vp(pipe["h"][slot].data_ptr()), ptr(r8), int(r8.numel()), 1))
+                ev_out = torch.cuda.Event()
+                ev_out.record(down_s)
+                res.record_stream(down_s)
+                # the host-side copy out of the page-locked buffer runs on a helper thread
+                pending.append(copier.submit(finish, (slot, ev_out, fdt)))
             while pending:
-                yield finish(pending.pop(0))
+                yield pending.pop(0).result()
 
     def _run(self, flag_windows, vis_windows):
         original = flag_windows.clone()

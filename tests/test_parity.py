@@ -668,7 +668,7 @@ def test_strategy_chain(backend):
     if not big(backend):
         for s in strategies:           # keep the emulated run short
             if s["task"] == "sum_threshold":
-                s["kwargs"].update(num_major_iterations=1, background_iterations=2)
+                s["kwargs"].update(num_major_iterations=1, background_iterations=1)
             if s["task"] == "uvcontsub_flagger":
                 s["kwargs"].update(major_cycles=2)
     got = common.run_strategies(tb, strategies, vis, flags, ubl, ants, masks, cf, cw)

@@ -994,7 +994,12 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         if (b.medians) b.medians += r0;
         if (b.uv_unflagged) b.uv_unflagged += r0;
         b.medbuf += r0;
-        TC_LAUNCH(k_brk_sample, nr, 1024, 0, c->stream, b, st + r0, todo + r0);
+#ifdef TC_EMU
+        const int sample_threads = 256;    // fewer fibers to switch between in the emulated build
+#else
+        const int sample_threads = 1024;
+#endif
+        TC_LAUNCH(k_brk_sample, nr, sample_threads, 0, c->stream, b, st + r0, todo + r0);
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + TC_BRK_SLICE - 1) / TC_BRK_SLICE);

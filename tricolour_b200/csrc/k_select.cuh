@@ -666,10 +666,10 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in,
 
 // ----------------------------------------------------------------------------
 // Bracket select: the exact median in two sweeps over the data instead of four.
-//   1. k_brk_sample   a stratified sample of 4096 keys per range is sorted in
-//                     shared memory; keys at sample ranks mid -+ delta bracket
-//                     the true median with overwhelming probability.  Ranges
-//                     of at most 4096 samples are sorted outright (exact).
+//   1. k_brk_sample   a stratified sample of 4096 keys per range is gathered in
+//                     shared memory; the keys at sample ranks mid -+ delta (two block
+//                     radix selects) bracket the true median with overwhelming
+//                     probability.  Ranges of at most 4096 samples are settled here.
 //   2. k_brk_collect  one sweep: count the keys below the bracket, copy the keys
 //                     inside it (a few percent) to a compact buffer.
 //   3. k_brk_select   radix select of rank (n/2 - below) inside the compact
@@ -694,10 +694,62 @@ __device__ __forceinline__ uint32_t brk_hash(uint32_t x)
     return x;
 }
 
+// key of rank `kth` (0-based) among keys[0, n) in shared memory: three 11/11/10-bit
+// radix passes with a shared histogram.  Every thread of the block calls it (256,
+// 512 or 1024 threads) and gets the result.
+__device__ __forceinline__ uint32_t block_select_smem(const uint32_t *keys, int n, uint32_t kth, uint32_t *hist,
+                                                      uint32_t *s_wsum, uint32_t *s_scal)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = TC_SEL_BINS / nt;            // bins per thread: 8, 4 or 2
+    uint32_t prefix = 0, himask = 0, remaining = kth;
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const uint32_t dmask = pass == 2 ? 1023u : 2047u;
+        for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            const uint32_t k = keys[i];
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
+        }
+        __syncthreads();
+        uint32_t loc[8];
+        uint32_t sum = 0;
+        for (int q = 0; q < per; q++) { loc[q] = hist[tid * per + q]; sum += loc[q]; }
+        uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+            if ((tid & 31) >= o) inc += v;
+        }
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < (tid >> 5); w++) woff += s_wsum[w];
+        const uint32_t excl = woff + inc - sum;
+        if (remaining >= excl && remaining < excl + sum) {
+            uint32_t acc = excl, digit = tid * per;
+            for (int q = 0; q < per; q++) {
+                if (remaining < acc + loc[q]) { digit = tid * per + q; break; }
+                acc += loc[q];
+            }
+            s_scal[0] = prefix | (digit << shift);
+            s_scal[1] = remaining - acc;
+        }
+        __syncthreads();
+        prefix = s_scal[0];
+        remaining = s_scal[1];
+        himask |= dmask << shift;
+        __syncthreads();
+    }
+    return prefix;
+}
+
 __global__ void __launch_bounds__(1024)
 k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo)
 {
     __shared__ uint32_t keys[TC_BRK_SAMPLES];
+    __shared__ uint32_t hist[TC_SEL_BINS];
+    __shared__ uint32_t s_wsum[32], s_scal[2];
     __shared__ int s_valid;
     const int range = blockIdx.x, tid = threadIdx.x;
     const int64_t lo = a.range_lo[range], hi = a.range_hi[range];
@@ -712,7 +764,7 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
         int64_t pos = -1;
         if (exact) { if (j < len) pos = lo + j; }
         else {
-            // stratified: one sample per stratum of len / 2048 elements
+            // stratified: one sample per stratum of len / 4096 elements
             int64_t s0 = (int64_t)j * len / TC_BRK_SAMPLES, s1 = (int64_t)(j + 1) * len / TC_BRK_SAMPLES;
             int64_t w = s1 - s0 > 0 ? s1 - s0 : 1;
             pos = lo + s0 + (int64_t)(brk_hash((uint32_t)j * 2654435761u ^ (uint32_t)range) % (uint32_t)w);
@@ -725,42 +777,40 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     }
     atomicAdd(&s_valid, nv);
     __syncthreads();
-    // bitonic sort of 2048 keys (invalid keys = 0xffffffff sink to the end)
-    for (int size = 2; size <= TC_BRK_SAMPLES; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < TC_BRK_SAMPLES / 2; t += (int)blockDim.x) {
-                int i = 2 * t - (t & (stride - 1));
-                int j = i + stride;
-                bool up = (i & size) == 0;
-                uint32_t x = keys[i], y = keys[j];
-                if ((x > y) == up) { keys[i] = y; keys[j] = x; }
-            }
-            __syncthreads();
+    // two order statistics of the sample are needed (invalid keys = 0xffffffff rank
+    // last): the middle pair of an exactly covered range, or the bracket ends
+    const int sv = s_valid;
+    const int nk = exact ? (int)len : TC_BRK_SAMPLES;
+    uint32_t ka = 0, kb = 0;
+    bool bracket = false;
+    if (exact) {
+        if (sv > 0) {
+            kb = block_select_smem(keys, nk, (uint32_t)(sv >> 1), hist, s_wsum, s_scal);
+            ka = (sv & 1) ? kb : block_select_smem(keys, nk, (uint32_t)((sv >> 1) - 1), hist, s_wsum, s_scal);
         }
+    } else if (sv >= 64) {
+        const int mid = sv >> 1;
+        const int delta = (int)(a.brk_k * sqrtf((float)sv)) + 4;
+        bracket = true;
+        ka = mid - delta >= 0 ? block_select_smem(keys, nk, (uint32_t)(mid - delta), hist, s_wsum, s_scal) : 0u;
+        kb = mid + delta < sv ? block_select_smem(keys, nk, (uint32_t)(mid + delta), hist, s_wsum, s_scal) : 0xfffffffeu;
+    }
     if (tid == 0) {
-        const int sv = s_valid;
         BrkState b;
         b.lo = 0; b.hi = 0xfffffffeu; b.n_valid = 0; b.n_below = 0; b.n_in = 0; b.done = 0; b.pad0 = b.pad1 = 0;
-        unsigned td = 0;
         if (exact) {
             double med = NAN;
-            if (sv > 0) {
-                float upper = key2f(keys[sv >> 1]);
-                float lower = (sv & 1) ? upper : key2f(keys[(sv >> 1) - 1]);
-                med = median_from_pair(lower, upper, sv);
-            }
+            if (sv > 0) med = median_from_pair(key2f(ka), key2f(kb), sv);
             a.medbuf[range] = med;
             if (a.medians) a.medians[range] = med;
             b.done = 1;
             b.n_valid = (uint32_t)sv;
-        } else if (sv >= 64) {
-            int mid = sv >> 1;
-            int delta = (int)(a.brk_k * sqrtf((float)sv)) + 4;
-            b.lo = mid - delta >= 0 ? keys[mid - delta] : 0u;
-            b.hi = mid + delta < sv ? keys[mid + delta] : 0xfffffffeu;
+        } else if (bracket) {
+            b.lo = ka;
+            b.hi = kb;
         }
         st[range] = b;
-        todo[range] = td;
+        todo[range] = 0;
     }
 }
 

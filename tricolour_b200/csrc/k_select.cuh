@@ -1006,17 +1006,19 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     const uint32_t base = s_base;
     for (uint32_t q = tid; q < cnt; q += nt)
         if ((int64_t)(base + q) < cap) out[base + q] = stage[q];
-    // the block that finishes a range last selects inside the range's compact buffer
-    __threadfence();
+    // the block that finishes a range last selects inside the range's compact buffer.
+    // The barrier orders the block's writes before thread 0's device-scope fence
+    // (fences are cumulative), the fence orders them before the ticket.
     __syncthreads();
     if (tid == 0) {
         const int64_t len = a.range_hi[range] - a.range_lo[range];
         const unsigned nactive = (unsigned)((len + TC_BRK_SLICE - 1) / TC_BRK_SLICE);
+        __threadfence();
         s_last = atomicAdd(&st[range].pad0, 1u) == nactive - 1 ? 1u : 0u;
+        __threadfence();
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     brk_select_tail(a, st, cbuf, cap, todo, range, stage, stage + TC_SEL_BINS, stage + TC_SEL_BINS + 64);
 }
 

@@ -308,6 +308,26 @@ def test_masked_gaussian_filter_radii(backend):
         assert_same(o, o2, "masked filter (thread per line) radii (%d, %d) shape %s" % (r0, r1, shape))
 
 
+def test_masked_gaussian_filter_dynamic_range(backend):
+    """samples spanning 60 decades (incl. float32 denormals and exact zeros): the
+    exact-division shortcut and the integer-pipe widening must still agree bit for bit"""
+    rs = np.random.RandomState(67)
+    shapes = [(64, 128), (32, 256)] if big(backend) else [(16, 24), (32, 16)]
+    for i, shape in enumerate(shapes):
+        for r0, r1 in ((4, 9), (10, 5), (17, 12)):
+            sig = np.array((_sigma_for_radius(r0), _sigma_for_radius(r1)))
+            d = (rs.uniform(0.5, 1.0, size=shape) * 10.0 ** rs.uniform(-33, 30, shape)).astype(np.float32)
+            d[rs.uniform(size=shape) < 0.05] = 0
+            d[rs.uniform(size=shape) < 0.05] = np.float32(1e-41)     # denormal
+            d[rs.uniform(size=shape) < 0.05] *= -1
+            fl = rs.uniform(size=shape) < 0.2
+            o = np.zeros_like(d)
+            G.masked_gaussian_filter(d, fl, sig, o)
+            o2 = np.zeros_like(d)
+            oracle.masked_gaussian_filter(d, fl, sig, o2)
+            assert_same(o, o2, "masked filter, wide dynamic range, radii (%d, %d) shape %s" % (r0, r1, shape))
+
+
 def test_get_background2d(backend):
     rs = np.random.RandomState(7)
     cases = [((95, 86), 1, (10., 10.), [0, 86]), ((45, 86), 3, (2.5, 2.5), [0, 40, 86]),

@@ -143,12 +143,12 @@ __device__ __forceinline__ float uv_abs_c64(float vx, float vy, float sx, float 
 // grid: (ceil(F / 2 / 256), T, cp); two channels per thread, no index divisions
 __global__ void __launch_bounds__(256)
 k_uv_absres(const float2 *__restrict__ vis, const float2 *__restrict__ smooth, int T, int F,
-            float *__restrict__ out)
+            float *__restrict__ out, int t0, int p0)
 {
     const int f = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (f >= F) return;
-    const int64_t cp = blockIdx.z;
-    const int64_t row = (cp * T + blockIdx.y) * (int64_t)F;
+    const int64_t cp = (int64_t)p0 + blockIdx.z;
+    const int64_t row = (cp * T + t0 + blockIdx.y) * (int64_t)F;
     const float2 *v = vis + row + f;
     const float2 *s = smooth + cp * F + f;
     if (f + 1 < F && (((uintptr_t)v | (uintptr_t)s) & 15) == 0 && (((uintptr_t)(out + row + f)) & 7) == 0) {

@@ -310,8 +310,14 @@ int tc_uvcontsub(tc_context *c, const void *vis, const uint8_t *flags, int64_t n
         TC_LAUNCH(k_uv_mean, dim3(tc_blocks_for(F, 256), (unsigned)ncp), 256, 0, c->stream, dvis, dout, (int)T,
                   (int)F, avg, unfl);
         TC_LAUNCH(k_uv_smooth, (unsigned)ncp, 256, 0, c->stream, avg, tw, (int)F, K, smooth);
-        TC_LAUNCH_NOSYNC(k_uv_absres, dim3(tc_blocks_for((F + 1) / 2, 256), (unsigned)T, (unsigned)ncp), 256, 0,
-                         c->stream, dvis, smooth, (int)T, (int)F, absres);
+        // grid (channel pairs, dumps, planes): at most 65535 in y and z per launch
+        for (int64_t p0 = 0; p0 < ncp; p0 += 65535)
+            for (int64_t t0 = 0; t0 < T; t0 += 65535) {
+                const unsigned np_ = (unsigned)(ncp - p0 < 65535 ? ncp - p0 : 65535);
+                const unsigned nt_ = (unsigned)(T - t0 < 65535 ? T - t0 : 65535);
+                TC_LAUNCH_NOSYNC(k_uv_absres, dim3(tc_blocks_for((F + 1) / 2, 256), nt_, np_), 256, 0, c->stream,
+                                 dvis, smooth, (int)T, (int)F, absres, (int)t0, (int)p0);
+            }
         tc_prof_end(c);
         c->launches += 3;
         ChunkSelectArgs s;

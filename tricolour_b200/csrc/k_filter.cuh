@@ -48,6 +48,7 @@ struct FilterArgs {
     const float *data2; // FOUT_RESID: the unfiltered samples in the output layout
     int flags_transposed;  // FIN_MASKED: `flags` is stored (plane, line, sample) instead of (plane, sample, line)
     int out_transposed;    // outputs are written (plane, line, sample): the layout change is fused into the drain
+    int single_axis;    // the only filtered axis of this filter (profile bucket only)
     float *gring;       // global delay-line scratch (when not in shared memory)
     int64_t gring_stride;
 };
@@ -262,7 +263,7 @@ static int launch_box_filter(tc_context *c, FilterArgs a)
 {
     if (a.nlines == 0 || a.n == 0) return TC_OK;
     a.div = tc_f32_pow4(2 * (int64_t)a.r + 1);
-    tc_prof_begin(c, TCP_BOX_FILTER);
+    tc_prof_begin(c, a.single_axis ? TCP_BOX_FILTER_1D : TCP_BOX_FILTER);
     const int64_t ngroups = (a.nlines + TC_FILT_LPW - 1) / TC_FILT_LPW;
     const size_t per_warp = ((size_t)2 * a.r * 32 + TC_FILT_WARP_FIXED) * sizeof(float);
     const size_t smem_cap = (size_t)c->smem_optin - 1024;

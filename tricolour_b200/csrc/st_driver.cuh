@@ -110,7 +110,7 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
             TC_TRY(launch_box_filter2(c, a));
         } else { a.data2 = data_FT; TC_TRY(launch_box_filter(c, a)); }
     } else if (r0 > 0) {
-        a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
+        a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0; a.single_axis = 1;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
         a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
         a.vout = out_FT;
@@ -121,7 +121,7 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
             c->launches++;
         }
     } else if (r1 > 0) {
-        a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
+        a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1; a.single_axis = 1;
         a.mode_in = FIN_MASKED; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
         a.data = data_FT; a.flags = w.fl_FT; a.vout = out_FT; a.data2 = data_FT;
         // T == 1: both layouts coincide and the lines are contiguous

@@ -76,10 +76,11 @@ struct tc_context {
 };
 
 enum { TCP_BOX_FILTER = 0, TCP_CHUNK_SELECT, TCP_LINE_MEDIAN, TCP_ST_SCAN, TCP_TRANSPOSE, TCP_PREP,
-       TCP_COMBINE, TCP_INTERP, TCP_ELEMENTWISE, TCP_UVCONTSUB, TCP_PACK, TCP_STATS, TCP_BOX_FILTER8, TCP_NIDS };
+       TCP_COMBINE, TCP_INTERP, TCP_ELEMENTWISE, TCP_UVCONTSUB, TCP_PACK, TCP_STATS, TCP_BOX_FILTER8, TCP_BOX_FILTER_1D,
+       TCP_NIDS };
 static const char *const tc_prof_names[TCP_NIDS] = {
     "box_filter", "chunk_select", "line_median", "st_scan", "transpose", "prep", "combine", "interp_nans",
-    "elementwise", "uvcontsub", "pack_unpack", "window_counts", "box_filter_axis0"};
+    "elementwise", "uvcontsub", "pack_unpack", "window_counts", "box_filter_axis0", "box_filter_single_axis"};
 
 static inline void tc_prof_begin(tc_context *c, int id)
 {

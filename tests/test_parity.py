@@ -291,7 +291,7 @@ def test_masked_gaussian_filter_radii(backend):
         oracle.masked_gaussian_filter(d, fl, sig, o2)
         assert_same(o, o2, "masked filter radii (%d, %d) shape %s" % (r0, r1, shape))
     # thread-per-line kernels: n % 16 == 0, every small radius (ring phases 2r mod 4)
-    t4 = [(r0, 4 + r0 % 3) for r0 in (1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 14)] + [(3, 2), (6, 3), (5, 5), (1, 1), (1, 9)]
+    t4 = [(r0, 4 + r0 % 3) for r0 in (1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 14)] + [(3, 2), (6, 3), (5, 5), (1, 1), (1, 9), (18, 5), (23, 6)]
     if big(backend):
         t4 += [(r0, r0 + 2) for r0 in (16, 21, 22, 28, 31, 32, 36)]
     for i, (r0, r1) in enumerate(t4):

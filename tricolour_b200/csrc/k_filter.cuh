@@ -49,6 +49,7 @@ struct FilterArgs {
     int flags_transposed;  // FIN_MASKED: `flags` is stored (plane, line, sample) instead of (plane, sample, line)
     int out_transposed;    // outputs are written (plane, line, sample): the layout change is fused into the drain
     int single_axis;    // the only filtered axis of this filter (profile bucket only)
+    int role;           // split first-axis kernels: 0 = value and weight blocks alternate, 1 = values only, 2 = weights only
     float *gring;       // global delay-line scratch (when not in shared memory)
     int64_t gring_stride;
 };

@@ -97,7 +97,13 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         a.vout = w.v_FT; a.wout = w.w_FT;
         a.data = data_TF;
         if (t4a_supported(c, a)) TC_TRY(launch_box_t4a(c, a));
-        else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
+        else if (lean0 && t4a_weights_supported(c, a)) {
+            // values: lane-per-chain kernel; weights: thread-per-line integer chains
+            a.role = 2;
+            TC_TRY(launch_box_t4a(c, a));
+            a.role = 1; a.data = data_FT;
+            TC_TRY(launch_box_filter2(c, a));
+        } else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
         else TC_TRY(launch_box_filter(c, a));
         memset(&a, 0, sizeof(a));
         a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;

@@ -913,6 +913,7 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
 // atomic per warp and iteration), then the block reserves its share of the
 // range's buffer with ONE global atomic and copies coalesced.
 #define TC_BRK_STAGE 8192
+template <bool TAKE_ABS, bool SKIP_NAN>
 __global__ void __launch_bounds__(1024)
 k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap,
               unsigned *__restrict__ todo)
@@ -958,17 +959,19 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
         int c = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            k4[q] = 0;
-            if (q < cntv && !((fw >> (8 * q)) & 0xffu)) {
-                float x = xv[q];
-                if (a.take_abs) x = fabsf(x - sub);
-                if (!(a.skip_nan && x != x)) {
-                    const uint32_t k = f2key(x);
-                    nvalid++;
-                    if (k < klo) nbelow++;
-                    else if (k <= khi) { in4[q] = true; k4[q] = k; c++; }
-                }
-            }
+            // predicated, no branches: the modes are template parameters
+            float x = xv[q];
+            if (TAKE_ABS) x = fabsf(x - sub);
+            bool valid = q < cntv && !((fw >> (8 * q)) & 0xffu);
+            if (SKIP_NAN) valid = valid && !(x != x);
+            const uint32_t k = f2key(x);
+            const bool below = valid && k < klo;
+            const bool inb = valid && !below && k <= khi;
+            nvalid += valid ? 1u : 0u;
+            nbelow += below ? 1u : 0u;
+            in4[q] = inb;
+            k4[q] = k;
+            c += inb ? 1 : 0;
         }
         // warp-level compaction: exclusive scan of the per-thread counts, one shared atomic per warp
         int inc = c;
@@ -1055,7 +1058,18 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + TC_BRK_SLICE - 1) / TC_BRK_SLICE);
-            TC_LAUNCH(k_brk_collect, dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap, cap, todo + r0);
+            if (b.take_abs && b.skip_nan)
+                TC_LAUNCH((k_brk_collect<true, true>), dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap,
+                          cap, todo + r0);
+            else if (b.take_abs)
+                TC_LAUNCH((k_brk_collect<true, false>), dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap,
+                          cap, todo + r0);
+            else if (b.skip_nan)
+                TC_LAUNCH((k_brk_collect<false, true>), dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap,
+                          cap, todo + r0);
+            else
+                TC_LAUNCH((k_brk_collect<false, false>), dim3(cslices, nr), 1024, 0, c->stream, b, st + r0, cbuf + r0 * cap,
+                          cap, todo + r0);
             c->launches++;
         }
     }

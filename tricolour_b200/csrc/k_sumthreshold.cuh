@@ -222,44 +222,70 @@ k_interp_nans_rows(const float *__restrict__ bg, const float *__restrict__ minue
     const float *x = bg + line * (int64_t)n;
     int *r = rv + line * (int64_t)n;
     const int ntiles = (n + 31) / 32;
+    // Both sweeps walk the row in tiles of 32 with a carried index; the samples of
+    // four tiles are loaded up front so that one memory latency covers four steps.
     // backward sweep: index of the next valid sample at or after i (n if none)
     int carry = n;
     int nnan = 0;
-    for (int t = ntiles - 1; t >= 0; t--) {
-        const int i = t * 32 + lane;
-        const bool valid = i < n && !(x[i] != x[i]);
-        const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
-        const unsigned mm = m >> lane;
-        if (i < n && !valid) r[i] = mm ? i + __ffs((int)mm) - 1 : carry;   // only NaN samples look it up
-        if (m) carry = t * 32 + __ffs((int)m) - 1;
-        nnan += (i < n && !valid) ? 1 : 0;
+    for (int t4 = ntiles - 1; t4 >= 0; t4 -= 4) {
+        float xs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = (t4 - u) * 32 + lane;
+            xs[u] = (t4 - u >= 0 && i < n) ? x[i] : NAN;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = t4 - u;
+            if (t < 0) break;
+            const int i = t * 32 + lane;
+            const bool valid = i < n && !(xs[u] != xs[u]);
+            const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
+            const unsigned mm = m >> lane;
+            if (i < n && !valid) r[i] = mm ? i + __ffs((int)mm) - 1 : carry;   // only NaN samples look it up
+            if (m) carry = t * 32 + __ffs((int)m) - 1;
+            nnan += (i < n && !valid) ? 1 : 0;
+        }
     }
     __syncwarp();
     // forward sweep: previous valid sample at or before i (-1 if none), then fill
     int carl = -1;
-    for (int t = 0; t < ntiles; t++) {
-        const int i = t * 32 + lane;
-        const float xi = i < n ? x[i] : 0.f;
-        const bool valid = i < n && !(xi != xi);
-        const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
-        const unsigned below = m & (0xffffffffu >> (31 - lane));
-        const int lv = below ? t * 32 + 31 - __clz((int)below) : carl;
-        if (m) carl = t * 32 + 31 - __clz((int)m);
-        if (i < n) {
-            float val = xi;
-            if (!valid) {
-                const int rr = r[i];
-                if (lv < 0 && rr >= n) val = 0.0f;
-                else if (lv < 0) val = x[rr];
-                else if (rr >= n) val = x[lv];
-                else {
-                    const float start = x[lv];
-                    // float32 difference, true division by an int64 -> float64
-                    const double grad = __ddiv_rn((double)(x[rr] - start), (double)(rr - lv));
-                    val = (float)__dadd_rn((double)start, __dmul_rn((double)(i - lv), grad));
+    for (int t4 = 0; t4 < ntiles; t4 += 4) {
+        float xs[4], ms[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = (t4 + u) * 32 + lane;
+            const bool in = t4 + u < ntiles && i < n;
+            xs[u] = in ? x[i] : 0.f;
+            ms[u] = (in && minuend) ? minuend[line * (int64_t)n + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = t4 + u;
+            if (t >= ntiles) break;
+            const int i = t * 32 + lane;
+            const float xi = xs[u];
+            const bool valid = i < n && !(xi != xi);
+            const unsigned m = __ballot_sync(TC_FULL_MASK, valid);
+            const unsigned below = m & (0xffffffffu >> (31 - lane));
+            const int lv = below ? t * 32 + 31 - __clz((int)below) : carl;
+            if (m) carl = t * 32 + 31 - __clz((int)m);
+            if (i < n) {
+                float val = xi;
+                if (!valid) {
+                    const int rr = r[i];
+                    if (lv < 0 && rr >= n) val = 0.0f;
+                    else if (lv < 0) val = x[rr];
+                    else if (rr >= n) val = x[lv];
+                    else {
+                        const float start = x[lv];
+                        // float32 difference, true division by an int64 -> float64
+                        const double grad = __ddiv_rn((double)(x[rr] - start), (double)(rr - lv));
+                        val = (float)__dadd_rn((double)start, __dmul_rn((double)(i - lv), grad));
+                    }
                 }
+                out[line * (int64_t)n + i] = minuend ? ms[u] - val : val;
             }
-            out[line * (int64_t)n + i] = minuend ? minuend[line * (int64_t)n + i] - val : val;
         }
     }
     (void)nnan;

@@ -391,7 +391,45 @@ __device__ __forceinline__ void st_window_mem(const float *__restrict__ d, const
     double c = 0.0;
     cum[0] = 0.0;
     int lastpos = -(1 << 30), lastneg = -(1 << 30);
-    for (int i = 0; i < m; i++) {
+    int i = 0;
+    // Blocks of four samples with all their loads issued up front (one memory latency
+    // per block instead of per sample).  cum[j .. j + 3] of a block were written by
+    // earlier blocks as soon as w >= 4, which holds for every width that gets here
+    // except 3 (widths 1, 2, 4, 8 use the register rings).
+    if (w >= 4) {
+        for (; i + 4 <= m; i += 4) {
+            float xs[4];
+            u8 si[4], sj[4];
+            double cj[4];
+            const int j0 = i + 1 - w;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                xs[k] = d[(int64_t)(i + k) * es];
+                si[k] = pin ? pin[(int64_t)(i + k) * ss] : (u8)0;
+                const int j = j0 + k;
+                cj[k] = j >= 0 ? cum[(int64_t)j * ss] : 0.0;
+                sj[k] = (pin && j >= 0) ? pin[(int64_t)j * ss] : (u8)0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                double x = (double)xs[k];
+                const u8 st = si[k];
+                if ((st & 1) && x > limit) x = limit;
+                else if ((st & 2) && x < -limit) x = -limit;
+                c = c + x;
+                cum[(int64_t)(i + k + 1) * ss] = c;
+                const int j = j0 + k;
+                if (j >= 0) {
+                    const double avg = c - cj[k];
+                    if (avg * sc > limit) lastpos = j;
+                    if (avg * nsc > limit) lastneg = j;
+                    const u8 add = (u8)(((j - lastpos < w) ? 1 : 0) | ((j - lastneg < w) ? 2 : 0));
+                    pout[(int64_t)j * ss] = (u8)(sj[k] | add);
+                }
+            }
+        }
+    }
+    for (; i < m; i++) {
         double x = (double)d[(int64_t)i * es];
         const u8 st = pin ? pin[(int64_t)i * ss] : (u8)0;
         if ((st & 1) && x > limit) x = limit;

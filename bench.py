@@ -5,7 +5,7 @@ bench.py -- throughput of the tricolour flagging hot path on B200.
 A "step" is one pass of the FULL default strategy (tricolour/conf/default.yaml:
 2x nan/zero flags, 2x static mask, 4 sum_threshold tasks = 8 SumThreshold passes,
 2 uvcontsub tasks = 17 cycles, flag_autos, combine_with_input_flags) over one
-block of synthetic MeerKAT-shaped windows: `--baselines` baselines (default 32:
+block of synthetic MeerKAT-shaped windows: `--baselines` baselines (default 64:
 the reference's `--baseline-chunks` option, app.py:189, whose default is 16;
 batches are sized to the GPU) x 4 correlations x 512 dumps x 4096
 channels of BASELINE.json's configs[1].  Every rank owns a different block of
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--baselines", type=int, default=32, help="baselines per step and rank (tricolour --baseline-chunks)")
+    ap.add_argument("--baselines", type=int, default=64, help="baselines per step and rank (tricolour --baseline-chunks)")
     ap.add_argument("--ntime", type=int, default=NTIME)
     ap.add_argument("--nchan", type=int, default=NCHAN)
     ap.add_argument("--cpu-baselines", type=int, default=0, help="baselines of the CPU sample (0 = auto)")

@@ -207,7 +207,7 @@ static size_t st_workspace_per_plane(int64_t T, int64_t F, int64_t Fa, int nchun
 static size_t tc_workspace_budget()
 {
     const char *e = getenv("TC_WORKSPACE_MB");
-    size_t mb = e ? (size_t)atoll(e) : 16384;
+    size_t mb = e ? (size_t)atoll(e) : 49152;
     if (mb < 64) mb = 64;
     return mb << 20;
 }

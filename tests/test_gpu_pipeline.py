@@ -201,3 +201,17 @@ def test_pipelined_executor_matches_block_by_block(cuda_lib):
         assert g.dtype == w.dtype and g.shape == w.shape
         assert np.array_equal(g, w)
     assert list(ex.apply_strategies_pipelined([])) == []
+
+
+@pytest.mark.gpu
+def test_plane_batching_is_invisible(cuda_lib, monkeypatch):
+    """tc_sum_threshold cuts the planes into batches that fit TC_WORKSPACE_MB; the
+    flags must not depend on where the cuts fall"""
+    vis, flags = common.make_windows(12, 4, 64, 1024, seed=77)
+    kw = dict(common.DEFAULT_STRATEGY_KW["final_st_broad"])
+    whole = tb.sum_threshold_flagger(vis, flags, **kw)
+    monkeypatch.setenv("TC_WORKSPACE_MB", "64")          # 48 planes x 64 Ki samples x ~50 B: several batches
+    cut = tb.sum_threshold_flagger(vis, flags, **kw)
+    assert np.array_equal(whole, cut)
+    sub = oracle.sum_threshold_flagger(vis[:1], flags[:1], **kw)
+    assert np.array_equal(whole[:1], sub)

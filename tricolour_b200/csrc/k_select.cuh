@@ -76,6 +76,17 @@ struct LineMedianArgs {
     u8 *out_flags;      // LM_TIME_MEDIAN: 1 where the line had no samples
 };
 
+// c += key < t as a compare and a predicated add (the compiler's own sequence is
+// three instructions on one dependency chain)
+__device__ __forceinline__ void lm_count_below(int &c, uint32_t key, uint32_t t)
+{
+#ifndef TC_EMU
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(key), "r"(t));
+#else
+    c += key < t ? 1 : 0;
+#endif
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(128)
 k_line_median(LineMedianArgs a)
@@ -141,10 +152,16 @@ k_line_median(LineMedianArgs a)
     uint32_t prefix = 0;
     for (int bit = 31; bit >= 0; bit--) {
         const uint32_t t = prefix | (1u << bit);
-        int c = 0;
+        // four independent partial counts (VPL is a multiple of 4): short dependency chains
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int k = 0; k < VPL; k++) c += key[k] < t ? 1 : 0;
-        c = warp_sum_i(c);
+        for (int k = 0; k < VPL; k += 4) {
+            lm_count_below(c0, key[k], t);
+            lm_count_below(c1, key[k + 1], t);
+            lm_count_below(c2, key[k + 2], t);
+            lm_count_below(c3, key[k + 3], t);
+        }
+        const int c = warp_sum_i((c0 + c1) + (c2 + c3));
         if (c <= kth) prefix = t;
     }
     // `prefix` is the key of the upper median; the lower one differs only when the

@@ -302,6 +302,9 @@ k_interp_nans_rows(const float *__restrict__ bg, const float *__restrict__ minue
 // padded sample, both laid out [chunk][sample][line] like the data.
 // ----------------------------------------------------------------------------
 #define TC_MAX_WINDOWS 16
+#ifndef TC_ST_MINBLOCKS
+#define TC_ST_MINBLOCKS 5   // 96 registers: measured best of 3..5 blocks of 128 threads per SM
+#endif
 struct StScanArgs {
     const float *data;
     const float *thr;         // [line*nchunks + chunk] float32 thresholds (inf = none)
@@ -670,7 +673,7 @@ __device__ __forceinline__ void st_fused_1248_v2(const float *__restrict__ d, u8
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TC_ST_MINBLOCKS)
 k_st_scan(StScanArgs a)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -95,9 +95,18 @@ k_line_median(LineMedianArgs a)
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nseg = a.seg_ends ? a.nseg : 1;
     if (warp >= a.nlines * nseg) return;
-    int64_t line = warp / nseg;
-    int seg = (int)(warp - line * nseg);
-    int64_t outer = line / a.ninner, inner = line - outer * a.ninner;
+    int64_t line, outer, inner;
+    int seg;
+    if (a.nlines * nseg < (int64_t)1 << 31) {
+        // 32-bit divisions are inline; 64-bit ones are subroutine calls
+        const unsigned w32 = (unsigned)warp, l32 = w32 / (unsigned)nseg, o32 = l32 / (unsigned)a.ninner;
+        line = l32; seg = (int)(w32 - l32 * (unsigned)nseg);
+        outer = o32; inner = l32 - o32 * (unsigned)a.ninner;
+    } else {
+        line = warp / nseg;
+        seg = (int)(warp - line * nseg);
+        outer = line / a.ninner; inner = line - outer * a.ninner;
+    }
     int64_t s0 = a.seg_ends ? a.seg_ends[seg] : 0;
     int n = a.seg_ends ? (int)(a.seg_ends[seg + 1] - s0) : a.n;
     int64_t base = outer * a.outer_stride + inner * a.inner_stride + s0 * a.elem_stride;

@@ -123,11 +123,12 @@ k_or_spec(u8 *__restrict__ flags, const u8 *__restrict__ spec, int64_t total, in
 __global__ void __launch_bounds__(256)
 k_or_spec_tf16(uint4 *__restrict__ flags, const uint4 *__restrict__ spec, int64_t total16, int T, int F16)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total16) return;
-    int64_t row = i / F16;
-    int f = (int)(i - row * F16);
-    int64_t cp = row / T;
+    // grid (ceil(F16 / 256), T, planes): no index divisions
+    (void)total16;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F16) return;
+    const int64_t cp = blockIdx.z;
+    const int64_t i = (cp * T + blockIdx.y) * (int64_t)F16 + f;
     const uint4 sp = spec[cp * F16 + f];
     if (sp.x | sp.y | sp.z | sp.w) {
         uint4 v = flags[i];
@@ -826,12 +827,13 @@ k_combine_time_v16(const uint4 *__restrict__ spec, const uint4 *__restrict__ tim
                    const uint4 *__restrict__ freq_f, int64_t total16, int T, int F16, int lo, int ext,
                    uint4 *__restrict__ out)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total16) return;
-    int64_t row = i / F16;
-    int f = (int)(i - row * F16);
-    int64_t cp = row / T;
-    int t = (int)(row - cp * T);
+    // grid (ceil(F16 / 256), T, planes): no index divisions
+    (void)total16;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F16) return;
+    const int64_t cp = blockIdx.z;
+    const int t = blockIdx.y;
+    const int64_t i = (cp * T + t) * (int64_t)F16 + f;
     uint4 any = make_uint4(0u, 0u, 0u, 0u);
     if (ext > 0) {
         any = spec[cp * F16 + f];
@@ -889,10 +891,12 @@ k_dilate_rows_v16(const uint4 *__restrict__ c1, int F16, int lo, int ext, uint4 
 __global__ void __launch_bounds__(128)
 k_colcnt_v4(const unsigned *__restrict__ d, int T, int F4, int64_t total4, int *__restrict__ colcnt)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
-    int64_t cp = i / F4;
-    int f = (int)(i - cp * F4);
+    // grid (ceil(F4 / 128), planes): no index divisions
+    (void)total4;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F4) return;
+    const int64_t cp = blockIdx.y;
+    const int64_t i = cp * F4 + f;
     const unsigned *p = d + cp * (int64_t)T * F4 + f;
     unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (int t0 = 0; t0 < T; t0 += 128) {
@@ -911,11 +915,13 @@ k_finalize_flags_v4(const unsigned *__restrict__ d, const int *__restrict__ rowc
                     int64_t total4, int T, int F4, double row_limit, double col_limit,
                     unsigned *__restrict__ out, unsigned *__restrict__ iter_flags)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
-    int64_t row = i / F4;
-    int f = (int)(i - row * F4);
-    int64_t cp = row / T;
+    // grid (ceil(F4 / 256), T, planes): no index divisions
+    (void)total4;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F4) return;
+    const int64_t cp = blockIdx.z;
+    const int64_t row = cp * T + blockIdx.y;
+    const int64_t i = row * F4 + f;
     unsigned w = d[i];
     if ((double)rowcnt[row] > row_limit) w = 0x01010101u;
     const int4 cc = colcnt[cp * F4 + f];

@@ -291,19 +291,21 @@ static int dev_combine_flags(tc_context *c, int64_t np, int T, int Fa, int F, in
     const bool vec16 = avg == 1 && (F & 15) == 0 && fe >= 0 && fe <= 16 && ((uintptr_t)vis & 15) == 0 &&
                        ((uintptr_t)out_flags & 3) == 0 && ((uintptr_t)iter_flags_accum & 3) == 0 &&
                        ((uintptr_t)spec_out & 15) == 0 && ((uintptr_t)time_TF & 15) == 0 &&
-                       ((uintptr_t)freq_TF & 15) == 0 && !getenv("TC_COMBINE_SCALAR");
+                       ((uintptr_t)freq_TF & 15) == 0 && T <= 65535 && np <= 65535 && !getenv("TC_COMBINE_SCALAR");
     if (vec16) {
         const int F16 = F / 16, F4 = F / 4;
-        TC_LAUNCH_NOSYNC(k_combine_time_v16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (const uint4 *)spec_out,
+        TC_LAUNCH_NOSYNC(k_combine_time_v16, dim3(tc_blocks_for(F16, 256), (unsigned)T, (unsigned)np), 256, 0, c->stream,
+                         (const uint4 *)spec_out,
                          (const uint4 *)time_TF, (const uint4 *)freq_TF, N / 16, T, F16, -(te / 2), te, (uint4 *)c1);
         c->launches++;
         TC_LAUNCH(k_dilate_rows_v16, (unsigned)(np * T), 256, (size_t)(F + 32), c->stream, (const uint4 *)c1, F16,
                   -(fe / 2), fe, (uint4 *)dflags, rowcnt);
         c->launches++;
-        TC_LAUNCH_NOSYNC(k_colcnt_v4, tc_blocks_for(np * (int64_t)F4, 128), 128, 0, c->stream,
+        TC_LAUNCH_NOSYNC(k_colcnt_v4, dim3(tc_blocks_for(F4, 128), (unsigned)np), 128, 0, c->stream,
                          (const unsigned *)dflags, T, F4, np * (int64_t)F4, colcnt);
         c->launches++;
-        TC_LAUNCH_NOSYNC(k_finalize_flags_v4, tc_blocks_for(NF / 4, 256), 256, 0, c->stream, (const unsigned *)dflags,
+        TC_LAUNCH_NOSYNC(k_finalize_flags_v4, dim3(tc_blocks_for(F4, 256), (unsigned)T, (unsigned)np), 256, 0, c->stream,
+                         (const unsigned *)dflags,
                          rowcnt, (const int4 *)colcnt, vis, vis_kind, NF / 4, T, F4, frac_f * (double)F,
                          (double)T * frac_t, (unsigned *)out_flags, (unsigned *)iter_flags_accum);
         c->launches++;
@@ -393,9 +395,10 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
                              p->windows_freq, p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
                              p->freq_chunk_ends, nce, spec_out));
     // flags |= spec_flags (flagging.py:954), both layouts
-    if ((Fa & 15) == 0 && (T & 15) == 0) {
+    if ((Fa & 15) == 0 && (T & 15) == 0 && T <= 65535 && np <= 65535) {
         // flag bytes are 0/1 (k_prep wrote them): OR whole vectors, in both layouts
-        TC_LAUNCH_NOSYNC(k_or_spec_tf16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (uint4 *)fl_TF,
+        TC_LAUNCH_NOSYNC(k_or_spec_tf16, dim3(tc_blocks_for(Fa / 16, 256), (unsigned)T, (unsigned)np), 256, 0, c->stream,
+                         (uint4 *)fl_TF,
                          (const uint4 *)spec_out, N / 16, T, Fa / 16);
         TC_LAUNCH_NOSYNC(k_or_spec_ft16, tc_blocks_for(N / 16, 256), 256, 0, c->stream, (uint4 *)fl_FT, spec_out,
                          N / 16, T / 16);

@@ -421,7 +421,7 @@ def ours(args):
             "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
             "flag_fraction": flag_frac,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
             cores = os.cpu_count() or 1
             threads = min(cores, 32)
             nblc = args.cpu_baselines or threads

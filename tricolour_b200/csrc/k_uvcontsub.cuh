@@ -82,8 +82,16 @@ k_uv_mean(const float2 *__restrict__ vis, const u8 *__restrict__ flags, int T, i
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&unflagged[cp], s_cnt);
 }
 
-// smooth = ifft(first K bins of fft(avg)); one block per plane
 #define TC_UV_MAXK 64
+// (k * f) mod F; 32-bit arithmetic (inline) whenever the product fits, which it
+// does for every realistic K (< 64) and F (< 2^26)
+__device__ __forceinline__ int uv_tw_index(int k, int f, int F)
+{
+    if ((int64_t)TC_UV_MAXK * F < ((int64_t)1 << 32)) return (int)(((unsigned)k * (unsigned)f) % (unsigned)F);
+    return (int)(((int64_t)k * f) % F);
+}
+
+// smooth = ifft(first K bins of fft(avg)); one block per plane
 __global__ void __launch_bounds__(256)
 k_uv_smooth(const float2 *__restrict__ avg, const double2 *__restrict__ tw, int F, int K,
             float2 *__restrict__ smooth)
@@ -96,7 +104,7 @@ k_uv_smooth(const float2 *__restrict__ avg, const double2 *__restrict__ tw, int 
     for (int k = 0; k < K; k++) {
         double re = 0.0, im = 0.0;
         for (int f = tid; f < F; f += blockDim.x) {
-            double2 w = tw[(int)(((int64_t)k * f) % F)];
+            double2 w = tw[uv_tw_index(k, f, F)];
             double ar = (double)a[f].x, ai = (double)a[f].y;
             // a * conj(w)
             re += ar * w.x + ai * w.y;
@@ -119,7 +127,7 @@ k_uv_smooth(const float2 *__restrict__ avg, const double2 *__restrict__ tw, int 
     for (int f = tid; f < F; f += blockDim.x) {
         double re = 0.0, im = 0.0;
         for (int k = 0; k < K; k++) {
-            double2 w = tw[(int)(((int64_t)k * f) % F)];
+            double2 w = tw[uv_tw_index(k, f, F)];
             re += X[k].x * w.x - X[k].y * w.y;
             im += X[k].x * w.y + X[k].y * w.x;
         }

@@ -368,8 +368,9 @@ def ours(args):
         barrier()
         t0 = time.perf_counter()
         res = None
+        done_at = []
         for res in ex.apply_strategies_pipelined(((hf, hv) for _ in range(args.steps)), device=local):
-            pass
+            done_at.append(round(time.perf_counter() - t0, 4))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -379,7 +380,7 @@ def ours(args):
         assert res.shape == (B, NCORR, T, F)
         e2e = {"value": world * nvis * args.steps / dt / 1e9, "unit": "GVis/s",
                "h2d_bytes_per_step": int(nvis * 9), "d2h_bytes_per_step": int(nvis),
-               "serial_value": nvis * args.steps / dt_serial / 1e9,
+               "serial_value": nvis * args.steps / dt_serial / 1e9, "block_done_s": done_at,
                "api": "tricolour_b200.StrategyExecutor.apply_strategies_pipelined(numpy (flags, vis) blocks): "
                       "apply_strategies of tricolour.apps.tricolour.strat_executor over a sequence of blocks, "
                       "pinned host buffers; every block is uploaded, flagged and downloaded inside the timed "

@@ -161,7 +161,7 @@ static int dev_background2d(tc_context *c, int64_t np, int T, int Fa, const floa
     BgWork w;
     tc_mark mark = tc_arena_mark(c);
     TC_TRY(dev_bg_work_alloc(c, N, two_axes, &w));
-    TC_CUDA(cudaMemcpyAsync(w.fl_FT, flags_FT, N, cudaMemcpyDeviceToDevice, c->stream));
+    TC_TRY(tc_copy_d2d(c, w.fl_FT, flags_FT, N));
     int bg_is_TF = 0;
     for (int it = 0; it <= iterations; it++) {
         int64_t r0 = T == 1 ? 0 : radii[2 * it], r1 = radii[2 * it + 1];

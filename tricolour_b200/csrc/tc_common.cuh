@@ -69,6 +69,7 @@ struct tc_context {
     // the host wait for the stream and serialise callers that use several streams
     enum { NSLAB = 4, SLAB_BYTES = 512 * 1024 };
     char *slab[NSLAB] = {nullptr, nullptr, nullptr, nullptr};
+    char *slab_dev[NSLAB] = {nullptr, nullptr, nullptr, nullptr};   // the same slabs as the device sees them
     cudaEvent_t slab_ev[NSLAB] = {nullptr, nullptr, nullptr, nullptr};
     bool slab_busy[NSLAB] = {false, false, false, false};
     int slab_cur = 0;
@@ -141,7 +142,27 @@ static inline void tc_slab_rotate(tc_context *c)
     c->slab_off = 0;
 }
 
-// host -> device copy of a small table, asynchronous with respect to the host
+#ifndef TC_EMU
+// copies a staged table out of the page-locked slab (read through its device
+// mapping) into device memory: 16 bytes per thread, then the byte tail
+__global__ void __launch_bounds__(256)
+k_upload_small(const unsigned char *src, unsigned char *dst, unsigned bytes, int vec)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const unsigned n16 = bytes >> 4;
+        if (i < n16) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        const unsigned t = (n16 << 4) + i;
+        if (i < 16 && t < bytes) dst[t] = src[t];
+    } else if (i < bytes) dst[i] = src[i];
+}
+#endif
+
+// host -> device copy of a small table, asynchronous with respect to the host.
+// The table is staged in a page-locked slab and fetched by a kernel of the
+// context's stream instead of the copy engine: a cudaMemcpyAsync would queue
+// behind whatever bulk upload another stream has in flight (the next block of a
+// pipelined executor: 4.8 GB, 90 ms) and stall the flagging kernels behind it.
 static int tc_upload_small(tc_context *c, const void *h, size_t bytes, void *d)
 {
     if (!bytes) return TC_OK;
@@ -149,20 +170,56 @@ static int tc_upload_small(tc_context *c, const void *h, size_t bytes, void *d)
     size_t need = tc_align(bytes, 16);
     if (c->slab_off + need <= (size_t)tc_context::SLAB_BYTES) {
         if (!c->slab[c->slab_cur]) {
-            void *p = nullptr;
-            if (cudaHostAlloc(&p, tc_context::SLAB_BYTES, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+            void *p = nullptr, *dp = nullptr;
+            if (cudaHostAlloc(&p, tc_context::SLAB_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+                p = nullptr;
+            if (p && (cudaHostGetDevicePointer(&dp, p, 0) != cudaSuccess || !dp)) { cudaFreeHost(p); p = nullptr; }
             c->slab[c->slab_cur] = (char *)p;
+            c->slab_dev[c->slab_cur] = (char *)dp;
+            cudaGetLastError();
         }
         if (c->slab[c->slab_cur]) {
             char *stage = c->slab[c->slab_cur] + c->slab_off;
+            const unsigned char *stage_dev = (const unsigned char *)c->slab_dev[c->slab_cur] + c->slab_off;
             memcpy(stage, h, bytes);
             c->slab_off += need;
-            TC_CUDA(cudaMemcpyAsync(d, stage, bytes, cudaMemcpyHostToDevice, c->stream));
+            const int vec = ((uintptr_t)d & 15) == 0;
+            const unsigned nthreads = vec ? (unsigned)(bytes >> 4) + 16u : (unsigned)bytes;
+            k_upload_small<<<(nthreads + 255) / 256, 256, 0, c->stream>>>(stage_dev, (unsigned char *)d, (unsigned)bytes, vec);
+            TC_KERNEL_CHECK();
+            c->launches++;
             return TC_OK;
         }
     }
 #endif
     TC_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return TC_OK;
+}
+
+// device -> device copy on the SMs (the copy engines stay free for the bulk
+// transfers of other streams); both pointers 16-byte aligned
+__global__ void __launch_bounds__(256)
+k_copy_bytes(const unsigned char *src, unsigned char *dst, int64_t bytes)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n16 = bytes >> 4;
+    if (i < n16) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    const int64_t t = (n16 << 4) + i;
+    if (i < 16 && t < bytes) dst[t] = src[t];
+}
+
+static int tc_copy_d2d(tc_context *c, void *dst, const void *src, int64_t bytes)
+{
+    if (bytes <= 0) return TC_OK;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) != 0) {
+        TC_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, c->stream));
+        return TC_OK;
+    }
+    const int64_t nthreads = (bytes >> 4) + 16;
+    TC_LAUNCH_NOSYNC(k_copy_bytes, (unsigned)((nthreads + 255) / 256), 256, 0, c->stream, (const unsigned char *)src,
+                     (unsigned char *)dst, bytes);
+    c->launches++;
+    TC_KERNEL_CHECK();
     return TC_OK;
 }
 

@@ -632,7 +632,7 @@ int tc_stage_masked_filter(tc_context *c, const float *data, const uint8_t *flag
     TC_TRY(stage_planes(c, data, flags, ncp, T, F, space, &s));
     BgWork w;
     TC_TRY(dev_bg_work_alloc(c, n, true, &w));
-    TC_CUDA(cudaMemcpyAsync(w.fl_FT, s.f_FT, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    TC_TRY(tc_copy_d2d(c, w.fl_FT, s.f_FT, (int64_t)n));
     float *o_FT, *o_TF;
     TC_TRY(tc_alloc(c, (size_t)n, &o_FT));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)n, space, &o_TF));

@@ -9,6 +9,10 @@ host memory.  Here a block is uploaded once, all tasks run on the GPU against
 the resident visibilities and flags with the reference's combine rule per task
 (OR / replace), and only the final flags come back.
 """
+import os
+import sys
+import time
+
 import numpy as np
 
 from . import _cabi
@@ -135,19 +139,45 @@ class StrategyExecutor(object):
                 # does not wait (torch would treat foreign page-locked memory as pageable)
                 check(lib.tc_memcpy_async(up_ctx.handle, ptr(b["f"][slot]), ptr(f8), int(f8.nbytes), 0))
                 check(lib.tc_memcpy_async(up_ctx.handle, ptr(b["v"][slot]), ptr(v_np), int(v_np.nbytes), 0))
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=trace is not None)
                 ev.record(up_s)
+                if trace is not None:
+                    trace.append(("upload %d enqueued (host)" % k, time.perf_counter()))
+                    trace.append(("upload %d done" % k, ev))
                 return slot, ev, f_np.dtype, (f8, v_np)      # keep the sources alive until the copy ran
-
-            def finish(item):
-                slot, ev, fdt = item
-                ev.synchronize()
-                out = pipe["h"][slot].numpy().copy()     # the page-locked buffer is reused
-                return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
 
             from concurrent.futures import ThreadPoolExecutor
             copier = pipe.setdefault("copier", ThreadPoolExecutor(max_workers=1))
+            slicers = pipe.setdefault("slicers", ThreadPoolExecutor(max_workers=8))
 
+            def prepare(shape):
+                # the caller's array is allocated and its pages are touched on the helper thread
+                # while the block is being flagged
+                out = np.empty(shape, np.uint8)
+                out.reshape(-1)[::4096] = 0
+                return out
+
+            def finish(item):
+                slot, ev, fdt, prep = item
+                out = prep.result()
+                src = pipe["h"][slot].numpy()            # the page-locked buffer is reused
+                flat_o, flat_s = out.reshape(-1), src.reshape(-1)
+                ev.synchronize()
+                # once the download has landed only a plain copy is left, cut into slices for a
+                # few threads (numpy releases the GIL while copying)
+                n = flat_o.size
+                ncut = 8 if n >= (1 << 24) else 1
+                cuts = [n * i // ncut for i in range(ncut + 1)]
+                list(slicers.map(lambda i: np.copyto(flat_o[cuts[i]:cuts[i + 1]], flat_s[cuts[i]:cuts[i + 1]]),
+                                 range(ncut)))
+                return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
+
+            # TC_PIPE_TRACE=1 prints a timeline (device events and host times) after the last block
+            trace = [] if os.environ.get("TC_PIPE_TRACE") else None
+            if trace is not None:
+                t_host0 = time.perf_counter()
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(main)
             it = iter(blocks)
             pending = []          # futures of downloads in flight
             k = 0
@@ -166,21 +196,36 @@ class StrategyExecutor(object):
                 except StopIteration:
                     nxt = None
                 slot, ev_up, fdt, _src = cur
+                prep = copier.submit(prepare, tuple(pipe["f"][slot].shape))
                 main.wait_event(ev_up)
+                if trace is not None:
+                    ev_start = torch.cuda.Event(enable_timing=True)
+                    ev_start.record(main)
+                    trace.append(("flag %d start" % (k - 1), ev_start))
                 res = self._run(pipe["f"][slot].view(torch.bool), pipe["v"][slot])
-                ev_done = torch.cuda.Event()
+                ev_done = torch.cuda.Event(enable_timing=trace is not None)
                 ev_done.record(main)
+                if trace is not None:
+                    trace.append(("flag %d enqueued (host)" % (k - 1), time.perf_counter()))
+                    trace.append(("flag %d done" % (k - 1), ev_done))
                 pipe["free"][slot] = ev_done
                 down_s.wait_event(ev_done)
                 r8 = res.view(torch.uint8)
                 check(lib.tc_memcpy_async(down_ctx.handle, _cabi._vp(pipe["h"][slot].data_ptr()), ptr(r8), int(r8.numel()), 1))
-                ev_out = torch.cuda.Event()
+                ev_out = torch.cuda.Event(enable_timing=trace is not None)
                 ev_out.record(down_s)
+                if trace is not None:
+                    trace.append(("download %d done" % (k - 1), ev_out))
                 res.record_stream(down_s)
                 # the host-side copy out of the page-locked buffer runs on a helper thread
-                pending.append(copier.submit(finish, (slot, ev_out, fdt)))
+                pending.append(copier.submit(finish, (slot, ev_out, fdt, prep)))
             while pending:
                 yield pending.pop(0).result()
+            if trace is not None:
+                trace.append(("all results handed over (host)", time.perf_counter()))
+                for name, what in trace:
+                    ms = (what - t_host0) * 1e3 if isinstance(what, float) else ev0.elapsed_time(what)
+                    sys.stderr.write("pipe trace %9.1f ms  %s\n" % (ms, name))
 
     def _run(self, flag_windows, vis_windows):
         original = flag_windows.clone()

@@ -964,6 +964,7 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     // sample vector (the slice start is 4-aligned whenever the range start is)
     const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
     const int64_t step = vec ? (int64_t)nt * 4 : nt;
+    const unsigned lt = (1u << lane) - 1u;
     for (int64_t i0 = lo; i0 < hi; i0 += step) {
         uint32_t k4[4];
         bool in4[4] = {false, false, false, false};
@@ -983,7 +984,6 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
                 else fw |= 1u << (8 * q);
             }
         }
-        int c = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             // predicated, no branches: the modes are template parameters
@@ -998,23 +998,29 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
             nbelow += below ? 1u : 0u;
             in4[q] = inb;
             k4[q] = k;
-            c += inb ? 1 : 0;
         }
-        // warp-level compaction: exclusive scan of the per-thread counts, one shared atomic per warp
-        int inc = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(TC_FULL_MASK, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int total = __shfl_sync(TC_FULL_MASK, inc, 31);
-        if (total) {
+        // warp-level compaction by ballots: one shared atomic per warp and iteration reserves
+        // the warp's slots; a key's slot is the number of in-bracket keys of the earlier
+        // sub-samples q plus those of the same q in lower lanes.  The order of the keys in
+        // the stage does not matter to the select.
+        const unsigned m0 = __ballot_sync(TC_FULL_MASK, in4[0]), m1 = __ballot_sync(TC_FULL_MASK, in4[1]);
+        const unsigned m2 = __ballot_sync(TC_FULL_MASK, in4[2]), m3 = __ballot_sync(TC_FULL_MASK, in4[3]);
+        if (m0 | m1 | m2 | m3) {
+            const uint32_t n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
+            const uint32_t total = (n0 + n1) + (n2 + n3);
             uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(&s_in, (uint32_t)total);
-            base = __shfl_sync(TC_FULL_MASK, base, 31);
-            uint32_t slot = base + (uint32_t)(inc - c);
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (in4[q]) { if (slot < TC_BRK_STAGE) stage[slot] = k4[q]; slot++; }
+            if (lane == 0) base = atomicAdd(&s_in, total);
+            base = __shfl_sync(TC_FULL_MASK, base, 0);
+            // a stage that overflows is never read (the range goes to the radix fallback)
+            if (base + total <= TC_BRK_STAGE) {
+                // slots first, then four predicated stores
+                const uint32_t p0 = base + __popc(m0 & lt), p1 = base + n0 + __popc(m1 & lt);
+                const uint32_t p2 = base + n0 + n1 + __popc(m2 & lt), p3 = base + n0 + n1 + n2 + __popc(m3 & lt);
+                if (in4[0]) stage[p0] = k4[0];
+                if (in4[1]) stage[p1] = k4[1];
+                if (in4[2]) stage[p2] = k4[2];
+                if (in4[3]) stage[p3] = k4[3];
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

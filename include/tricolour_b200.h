@@ -65,6 +65,16 @@ const char *tc_profile_name(int id);
 int tc_profile_read(tc_context *ctx, int id, double *total_ms, long long *launches);
 /* workspace high-water mark in bytes */
 size_t tc_workspace_peak(tc_context *ctx);
+/* device memory the context's arena holds right now, and the context's share of the
+ * DEVICE-WIDE workspace budget (environment TC_WORKSPACE_MB, default 49152): the budget is
+ * divided between the contexts that hold an arena on the device, because the reference
+ * calls these functions from ThreadPool(nworkers) threads (apps/tricolour/app.py:266-271)
+ * and every thread owns a context.  tc_sum_threshold sizes its plane batches to the share;
+ * an arena that outgrew the share is released at the start of the next call. */
+size_t tc_workspace_held(tc_context *ctx);
+size_t tc_workspace_share(tc_context *ctx);
+/* waits for the context's stream and hands the arena back to the driver */
+int tc_context_trim(tc_context *ctx);
 int tc_alloc_pinned(size_t nbytes, void **out);
 int tc_free_pinned(void *ptr);
 /* asynchronous copy on the context's stream: kind 0 = host -> device, 1 = device -> host.

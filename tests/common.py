@@ -163,3 +163,54 @@ def run_strategies(mod, strategies, vis, flags, ubl, antspos, masks, chan_freq, 
         else:
             raise ValueError(task)
     return flags
+
+
+def run_strategies_planes(mod, strategies, vis, flags, ubl, antspos, masks, chan_freq, chan_width,
+                          threads=None):
+    """``run_strategies`` plane by plane in a ThreadPool (the reference's execution
+    model, app.py:266-271).  Every (baseline, correlation) plane is independent in
+    every task of the path, so this returns what one call on the whole block returns;
+    it is how the full-size parity tests and bench.py's parity check keep the CPU
+    oracle's run time down to seconds per plane."""
+    import os
+    from multiprocessing.pool import ThreadPool
+    nbl, ncorr = vis.shape[:2]
+    out = np.empty(flags.shape, flags.dtype)
+    jobs = [(b, c) for b in range(nbl) for c in range(ncorr)]
+
+    def work(bc):
+        b, c = bc
+        out[b:b + 1, c:c + 1] = run_strategies(mod, strategies, vis[b:b + 1, c:c + 1], flags[b:b + 1, c:c + 1],
+                                               ubl[b:b + 1], antspos, masks, chan_freq, chan_width)
+
+    n = max(1, min(len(jobs), threads or (os.cpu_count() or 1)))
+    if n == 1:
+        for j in jobs:
+            work(j)
+    else:
+        with ThreadPool(n) as pool:
+            pool.map(work, jobs)
+    return out
+
+
+def pick_baselines(ubl, antspos, n):
+    """``n`` baseline rows of ``ubl`` that cover the cases the strategy treats
+    differently: an auto-correlation (flag_autos), the shortest and the longest
+    cross baseline (uvrange of the second static mask), then evenly spread ones."""
+    ubl = np.asarray(ubl)
+    d = np.sqrt(0.5 * ((antspos[ubl[:, 1]] - antspos[ubl[:, 2]]) ** 2).sum(axis=1))
+    auto = np.flatnonzero(ubl[:, 1] == ubl[:, 2])
+    cross = np.flatnonzero(ubl[:, 1] != ubl[:, 2])
+    picks = []
+    if auto.size:
+        picks.append(int(auto[0]))
+    if cross.size:
+        picks.append(int(cross[np.argmax(d[cross])]))
+        picks.append(int(cross[np.argmin(d[cross])]))
+    for i in np.linspace(0, ubl.shape[0] - 1, max(n, 1)).astype(int):
+        picks.append(int(i))
+    out = []
+    for p in picks:
+        if p not in out:
+            out.append(p)
+    return out[:n]

@@ -215,3 +215,81 @@ def test_plane_batching_is_invisible(cuda_lib, monkeypatch):
     assert np.array_equal(whole, cut)
     sub = oracle.sum_threshold_flagger(vis[:1], flags[:1], **kw)
     assert np.array_equal(whole[:1], sub)
+
+
+@pytest.mark.gpu
+def test_pipelined_executor_single_refilled_pinned_buffer(cuda_lib):
+    """the usage INTEGRATION.md recommends: ONE page-locked (flags, vis) pair that the
+    generator refills in place for every block.  The executor must have finished reading
+    a block before it asks the generator for the next one."""
+    from tricolour_b200 import _cabi
+    nbl, T, F = 4, 64, 512
+    ubl = common.baselines(8)[:nbl].copy()
+    ants = common.antenna_layout(8)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    strategies = common.default_strategies()[:3]
+    ex = tb.StrategyExecutor(ants, ubl, cf, cw, masks, strategies)
+    blocks = [common.make_windows(nbl, 2, T, F, seed=190 + k, ubl=ubl) for k in range(5)]
+    want = [ex.apply_strategies(f, v) for v, f in blocks]
+    hv = _cabi.pinned_empty((nbl, 2, T, F), np.complex64)
+    hf = _cabi.pinned_empty((nbl, 2, T, F), np.bool_)
+
+    def gen():
+        for v, f in blocks:
+            hv[...] = v            # overwrites what the previous block was uploaded from
+            hf[...] = f
+            yield hf, hv
+
+    got = list(ex.apply_strategies_pipelined(gen()))
+    assert len(got) == len(want)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), "block %d" % k
+    _cabi.free_pinned(hv)
+    _cabi.free_pinned(hf)
+
+
+@pytest.mark.gpu
+def test_mixed_host_and_device_arguments_are_rejected(cuda_lib):
+    import torch
+    vis, flags = common.make_windows(1, 1, 16, 64, seed=5)
+    dv = torch.from_numpy(vis).cuda()
+    with pytest.raises(TypeError):
+        tb.sum_threshold_flagger(dv, flags)
+    with pytest.raises(TypeError):
+        tb.uvcontsub_flagger(vis, torch.from_numpy(flags).cuda())
+    with pytest.raises(TypeError):
+        tb.flag_nans_and_zeros(dv, flags)
+
+
+@pytest.mark.gpu
+def test_workspace_budget_is_shared_between_thread_contexts(cuda_lib, monkeypatch):
+    """every worker thread owns a context; together they must stay inside
+    TC_WORKSPACE_MB instead of each growing to the whole budget"""
+    import threading
+    from tricolour_b200 import _cabi
+    monkeypatch.setenv("TC_WORKSPACE_MB", "2048")
+    vis, flags = common.make_windows(4, 4, 64, 1024, seed=78)
+    kw = dict(common.DEFAULT_STRATEGY_KW["final_st_broad"])
+    want = tb.sum_threshold_flagger(vis, flags, **kw)
+    held, outs, shares = [], [], []
+    gate = threading.Barrier(4)
+
+    def work():
+        out = tb.sum_threshold_flagger(vis, flags, **kw)
+        gate.wait()                       # all four arenas alive at the same time
+        ctx = _cabi.get_context()
+        held.append(ctx.workspace_held())
+        shares.append(ctx.workspace_share())
+        out2 = tb.sum_threshold_flagger(vis, flags, **kw)
+        outs.append((out, out2))
+        _cabi.release_contexts()
+
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(outs) == 4
+    for a, b in outs:
+        assert np.array_equal(a, want) and np.array_equal(b, want)
+    assert sum(held) <= 2048 << 20
+    assert max(shares) <= (2048 << 20) // 4

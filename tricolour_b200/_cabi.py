@@ -64,6 +64,9 @@ _SIGNATURES = {
     "tc_synchronize": (_int, [_vp]),
     "tc_launch_count": (ctypes.c_ulonglong, [_vp]),
     "tc_workspace_peak": (ctypes.c_size_t, [_vp]),
+    "tc_workspace_held": (ctypes.c_size_t, [_vp]),
+    "tc_workspace_share": (ctypes.c_size_t, [_vp]),
+    "tc_context_trim": (_int, [_vp]),
     "tc_profile_enable": (_int, [_vp, _int]),
     "tc_profile_reset": (_int, [_vp]),
     "tc_profile_count": (_int, []),
@@ -176,6 +179,19 @@ class Context(object):
     def workspace_peak(self):
         return int(load().tc_workspace_peak(self._h))
 
+    def workspace_held(self):
+        """bytes of device memory this context's arena holds right now"""
+        return int(load().tc_workspace_held(self._h))
+
+    def workspace_share(self):
+        """this context's share of the device-wide workspace budget (TC_WORKSPACE_MB
+        divided between the contexts that hold an arena on the device)"""
+        return int(load().tc_workspace_share(self._h))
+
+    def trim(self):
+        """hand the arena back to the driver (waits for the context's stream)"""
+        check(load().tc_context_trim(self._h))
+
     def profile(self, on=True):
         check(load().tc_profile_enable(self._h, 1 if on else 0))
 
@@ -213,20 +229,39 @@ def default_device():
 
 
 _tls = threading.local()
+MAX_CACHED_CONTEXTS = 8      # per thread; the least recently used one is closed beyond that
 
 
 def get_context(device=None, stream=None):
     """Thread-local context for (device, stream); the reference is called from a
-    dask ThreadPool, so every worker thread gets its own stream and arena."""
+    dask ThreadPool, so every worker thread gets its own stream and arena.  A
+    thread keeps at most ``MAX_CACHED_CONTEXTS`` contexts (callers that bind work
+    to short-lived torch streams would otherwise pile up arenas): the least
+    recently used one is closed, which returns its arena to the driver."""
     if device is None:
         device = default_device()
     key = (int(device), int(stream) if stream else 0)
     cache = _tls.__dict__.setdefault("ctx", {})
-    ctx = cache.get(key)
+    ctx = cache.pop(key, None)
     if ctx is None:
         ctx = Context(device, stream)
-        cache[key] = ctx
+        while len(cache) >= MAX_CACHED_CONTEXTS:
+            old = cache.pop(next(iter(cache)))
+            old.close()
+    cache[key] = ctx         # most recently used last
     return ctx
+
+
+def release_contexts(trim_only=False):
+    """Close (or, with ``trim_only``, just empty the arenas of) the calling
+    thread's cached contexts.  Worker threads that are done flagging call this to
+    give their share of the device workspace back."""
+    cache = _tls.__dict__.get("ctx", {})
+    for key in list(cache):
+        if trim_only:
+            cache[key].trim()
+        else:
+            cache.pop(key).close()
 
 
 # ---------------------------------------------------------------------------
@@ -259,12 +294,22 @@ def torch_stream_handle(device_index):
 def context_for(*arrays):
     """Host arrays -> thread default context; device tensors -> a context bound
     to torch's current stream on the tensors' device."""
-    for a in arrays:
-        if is_device_array(a):
-            import torch
-            dev = a.device.index if a.device.index is not None else torch.cuda.current_device()
-            return get_context(dev, torch_stream_handle(dev)), DEVICE
-    return get_context(), HOST
+    arrays = [a for a in arrays if a is not None]
+    on_dev = [a for a in arrays if is_device_array(a)]
+    if not on_dev:
+        return get_context(), HOST
+    # the kernels take raw pointers: one host array (or a tensor of another GPU) among
+    # device tensors would be dereferenced as a device pointer
+    if len(on_dev) != len(arrays):
+        raise TypeError("tricolour_b200: arrays of one call must all be numpy arrays or all be "
+                        "CUDA tensors (got a mix of host and device arrays)")
+    import torch
+    devs = {a.device.index if a.device.index is not None else torch.cuda.current_device() for a in on_dev}
+    if len(devs) != 1:
+        raise ValueError("tricolour_b200: the CUDA tensors of one call live on different devices: %s"
+                         % sorted(devs))
+    dev = devs.pop()
+    return get_context(dev, torch_stream_handle(dev)), DEVICE
 
 
 _pinned = {}

@@ -1068,12 +1068,11 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     TC_TRY(tc_alloc(c, (size_t)nranges, &todo));
     if (!a.medbuf) TC_TRY(tc_alloc(c, (size_t)nranges, &a.medbuf));
     const bool small = max_range <= TC_BRK_SAMPLES;
-    a.brk_k = getenv("TC_BRK_K") ? (float)atof(getenv("TC_BRK_K")) : 1.75f;   // +-3.5 sigma of the sample rank of the median
+    static const float env_brk_k = getenv("TC_BRK_K") ? (float)atof(getenv("TC_BRK_K")) : 1.75f;
+    a.brk_k = env_brk_k;   // +-3.5 sigma of the sample rank of the median
     a.brk_slice = TC_BRK_SLICE;
-    if (getenv("TC_BRK_SLICE")) {
-        const int v = atoi(getenv("TC_BRK_SLICE"));
-        if (v >= 4096 && v <= (1 << 20)) a.brk_slice = v & ~4095;
-    }
+    static const int env_brk_slice = getenv("TC_BRK_SLICE") ? atoi(getenv("TC_BRK_SLICE")) : 0;
+    if (env_brk_slice >= 4096 && env_brk_slice <= (1 << 20)) a.brk_slice = env_brk_slice & ~4095;
     const int64_t cap = small ? 1 : max_range / 4 + 4096;
     uint32_t *cbuf = nullptr;
     if (!small) TC_TRY(tc_alloc(c, (size_t)nranges * cap, &cbuf));
@@ -1113,7 +1112,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     }
     tc_prof_end(c);
     TC_KERNEL_CHECK();
-    if (!small && getenv("TC_DEBUG_SELECT")) {
+    if (!small && TC_ENV_FLAG("TC_DEBUG_SELECT")) {
         std::vector<unsigned> h((size_t)nranges);
         std::vector<BrkState> hs((size_t)nranges);
         cudaStreamSynchronize(c->stream);
@@ -1174,7 +1173,7 @@ fallback_done:
 static int launch_chunk_select(tc_context *c, const ChunkSelectArgs &a, int64_t nranges, int64_t max_range)
 {
     if (nranges == 0) return TC_OK;
-    if (!getenv("TC_SELECT_RADIX")) return launch_bracket_select(c, a, nranges, max_range);
+    if (!TC_ENV_FLAG("TC_SELECT_RADIX")) return launch_bracket_select(c, a, nranges, max_range);
     // reference implementation of the select (kept for A/B checks): plain radix select
     if (max_range > 8 * TC_SEL_SLICE || (max_range > TC_SEL_SLICE && nranges < 2 * (int64_t)c->sm_count))
         return launch_chunk_select_multi(c, a, nranges, max_range);

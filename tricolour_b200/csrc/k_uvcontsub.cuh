@@ -33,10 +33,10 @@ k_uv_twiddle(double2 *__restrict__ tw, int F)
 // Also counts the unflagged samples of every plane.
 __global__ void __launch_bounds__(256)
 k_uv_mean(const float2 *__restrict__ vis, const u8 *__restrict__ flags, int T, int F,
-          float2 *__restrict__ avg, int *__restrict__ unflagged)
+          float2 *__restrict__ avg, int *__restrict__ unflagged, int64_t cp0)
 {
     __shared__ int s_cnt;
-    int64_t cp = blockIdx.y;
+    int64_t cp = cp0 + blockIdx.y;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -98,7 +98,7 @@ k_uv_smooth(const float2 *__restrict__ avg, const double2 *__restrict__ tw, int 
 {
     __shared__ double2 X[TC_UV_MAXK];
     __shared__ double2 red[8];
-    int64_t cp = blockIdx.x;
+    int64_t cp = blockIdx.x;     // gridDim.x goes up to 2^31 - 1
     const float2 *a = avg + cp * F;
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int k = 0; k < K; k++) {

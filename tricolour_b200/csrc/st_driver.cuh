@@ -254,7 +254,7 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     s.chunk_ends = d_ce; s.nwin = nwin; s.maxw = (int)maxw; s.mpad = mpad;
     for (int k = 0; k < nwin; k++) { s.windows[k] = windows[k]; s.tf[k] = tf[k]; s.scale[k] = scale[k]; }
     s.fused1248 = (nwin == 4 && windows[0] == 1 && windows[1] == 2 && windows[2] == 4 && windows[3] == 8 &&
-                   !getenv("TC_ST_UNFUSED")) ? (getenv("TC_ST_V1") ? 1 : 2) : 0;
+                   !TC_ENV_FLAG("TC_ST_UNFUSED")) ? (TC_ENV_FLAG("TC_ST_V1") ? 1 : 2) : 0;
     bool need_cum = false;
     for (int k = 0; k < nwin; k++)
         if (windows[k] != 1 && windows[k] != 2 && windows[k] != 4 && windows[k] != 8) need_cum = true;
@@ -291,7 +291,8 @@ static int dev_combine_flags(tc_context *c, int64_t np, int T, int Fa, int F, in
     const bool vec16 = avg == 1 && (F & 15) == 0 && fe >= 0 && fe <= 16 && ((uintptr_t)vis & 15) == 0 &&
                        ((uintptr_t)out_flags & 3) == 0 && ((uintptr_t)iter_flags_accum & 3) == 0 &&
                        ((uintptr_t)spec_out & 15) == 0 && ((uintptr_t)time_TF & 15) == 0 &&
-                       ((uintptr_t)freq_TF & 15) == 0 && T <= 65535 && np <= 65535 && !getenv("TC_COMBINE_SCALAR");
+                       ((uintptr_t)freq_TF & 15) == 0 && T <= 65535 && np <= 65535 && F + 32 <= 48 * 1024 &&
+                       np * (int64_t)T < ((int64_t)1 << 31) && !TC_ENV_FLAG("TC_COMBINE_SCALAR");
     if (vec16) {
         const int F16 = F / 16, F4 = F / 4;
         TC_LAUNCH_NOSYNC(k_combine_time_v16, dim3(tc_blocks_for(F16, 256), (unsigned)T, (unsigned)np), 256, 0, c->stream,

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <vector>
 #include <string>
+#include <atomic>
 
 typedef uint8_t u8;
 
@@ -44,6 +45,28 @@ static int tc_fail(int code, const char *fmt, ...)
         if (!(cond)) return tc_fail(TC_ERR_VALUE, __VA_ARGS__); \
     } while (0)
 
+// ------------------------------------------------------ environment knobs ----
+// read once per process (getenv walks the whole environment; the launch helpers sit on
+// the host path of every kernel launch)
+#define TC_ENV_FLAG(name)                                           \
+    ([]() -> bool {                                                 \
+        static const bool v = getenv(name) != nullptr;              \
+        return v;                                                   \
+    }())
+
+// ------------------------------------------------------- device ledger ------
+// The workspace budget is per DEVICE, not per context: dask's ThreadPool(nworkers)
+// gives every worker thread its own context (stream + arena), and each of them sizing
+// its plane batches to the whole budget would exhaust HBM.  The ledger counts the
+// contexts that hold an arena and the bytes they hold; tc_ws_share() divides
+// the budget between them.
+#define TC_MAX_DEVICES 64
+struct tc_device_ledger {
+    std::atomic<long long> arena_bytes{0};
+    std::atomic<int> arenas{0};
+};
+static tc_device_ledger g_tc_ledger[TC_MAX_DEVICES];
+
 // --------------------------------------------------------------- context ----
 struct tc_block { char *ptr; size_t size; };
 
@@ -54,6 +77,7 @@ struct tc_context {
     int sm_count = 148;
     int smem_optin = 227 * 1024;
     std::vector<tc_block> blocks;  // arena blocks; blocks[0] is the main one
+    size_t held = 0;               // bytes of all arena blocks (mirrored in the device ledger)
     size_t cur_block = 0, cur_off = 0;
     size_t used_total = 0;         // bytes handed out since the last reset
     size_t peak = 0;
@@ -223,18 +247,85 @@ static int tc_copy_d2d(tc_context *c, void *dst, const void *src, int64_t bytes)
     return TC_OK;
 }
 
-// start of an API call: if the previous call overflowed into extra blocks,
-// fold everything into one block of the peak size.
+static inline tc_device_ledger &tc_ledger(const tc_context *c)
+{
+    return g_tc_ledger[(c->device >= 0 && c->device < TC_MAX_DEVICES) ? c->device : 0];
+}
+
+static void tc_arena_note_block(tc_context *c, char *p, size_t size)
+{
+    if (c->blocks.empty()) tc_ledger(c).arenas.fetch_add(1);
+    c->blocks.push_back({p, size});
+    c->held += size;
+    tc_ledger(c).arena_bytes.fetch_add((long long)size);
+}
+
+// hands the whole arena back to the driver (the stream must be idle)
+static void tc_arena_free_all(tc_context *c)
+{
+    if (c->blocks.empty()) return;
+    for (auto &b : c->blocks) cudaFree(b.ptr);
+    c->blocks.clear();
+    tc_ledger(c).arena_bytes.fetch_sub((long long)c->held);
+    tc_ledger(c).arenas.fetch_sub(1);
+    c->held = 0;
+    c->cur_block = 0; c->cur_off = 0; c->used_total = 0;
+}
+
+// device-wide workspace limit: TC_WORKSPACE_MB (default 48 GiB); read once per API call
+static size_t tc_workspace_limit()
+{
+    const char *e = getenv("TC_WORKSPACE_MB");
+    size_t mb = e ? (size_t)atoll(e) : 49152;
+    if (mb < 64) mb = 64;
+    return mb << 20;
+}
+
+// this context's share of the device-wide workspace: the limit divided by the number
+// of contexts that hold (or are about to hold) an arena on the device, and never more
+// than what the device can still give
+static size_t tc_ws_share(tc_context *c)
+{
+    int n = tc_ledger(c).arenas.load();
+    if (c->blocks.empty()) n++;
+    if (n < 1) n = 1;
+    size_t share = tc_workspace_limit() / (size_t)n;
+#ifndef TC_EMU
+    size_t fre = 0, tot = 0;
+    if (cudaMemGetInfo(&fre, &tot) == cudaSuccess) {
+        const size_t reserve = (size_t)256 << 20;
+        size_t avail = c->held + (fre > reserve ? fre - reserve : 0) / 10 * 9;
+        if (avail < share) share = avail;
+    } else {
+        cudaGetLastError();
+    }
+#endif
+    if (share < ((size_t)64 << 20)) share = (size_t)64 << 20;
+    return share;
+}
+
+// start of an API call: if the previous call overflowed into extra blocks, fold
+// everything into one block of the peak size; an arena that has outgrown the context's
+// share of the device (more worker threads have started since) is handed back.
 static int tc_arena_reset(tc_context *c)
 {
-    if (c->blocks.size() > 1) {
+    bool oversized = false;
+    if (c->held > ((size_t)256 << 20) && tc_ledger(c).arenas.load() > 1) {
+        // only other arenas on the device can shrink this context's share
+        const size_t share = tc_workspace_limit() / (size_t)tc_ledger(c).arenas.load();
+        oversized = c->held > share + (share >> 1);
+    }
+    if (c->blocks.size() > 1 || oversized) {
         TC_CUDA(cudaStreamSynchronize(c->stream));
-        for (auto &b : c->blocks) cudaFree(b.ptr);
-        c->blocks.clear();
-        size_t want = tc_align(c->peak + (c->peak >> 3), 1 << 20);
-        char *p = nullptr;
-        TC_CUDA(cudaMalloc((void **)&p, want));
-        c->blocks.push_back({p, want});
+        tc_arena_free_all(c);
+        if (!oversized) {
+            size_t want = tc_align(c->peak + (c->peak >> 3), 1 << 20);
+            char *p = nullptr;
+            TC_CUDA(cudaMalloc((void **)&p, want));
+            tc_arena_note_block(c, p, want);
+        } else {
+            c->peak = 0;
+        }
     }
     c->cur_block = 0;
     c->cur_off = 0;
@@ -262,9 +353,13 @@ static int tc_arena_alloc(tc_context *c, size_t bytes, void **out)
         size_t want = tc_align(bytes > (size_t)(64 << 20) ? bytes : (size_t)(64 << 20), 1 << 20);
         char *p = nullptr;
         cudaError_t e = cudaMalloc((void **)&p, want);
-        if (e != cudaSuccess)
-            return tc_fail(TC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-        c->blocks.push_back({p, want});
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return tc_fail(TC_ERR_CUDA, "cudaMalloc(%zu) failed: %s (arena holds %zu bytes; %d arenas hold %lld bytes on "
+                           "device %d; lower TC_WORKSPACE_MB or close idle contexts)", want, cudaGetErrorString(e),
+                           c->held, tc_ledger(c).arenas.load(), tc_ledger(c).arena_bytes.load(), c->device);
+        }
+        tc_arena_note_block(c, p, want);
     }
 }
 

@@ -59,7 +59,7 @@ void tc_context_destroy(tc_context *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto &b : c->blocks) cudaFree(b.ptr);
+    tc_arena_free_all(c);
 #ifndef TC_EMU
     for (int k = 0; k < tc_context::NSLAB; k++) {
         if (c->slab[k]) cudaFreeHost(c->slab[k]);
@@ -101,6 +101,22 @@ int tc_profile_read(tc_context *c, int id, double *ms, long long *count)
     return TC_OK;
 }
 size_t tc_workspace_peak(tc_context *c) { return c->peak; }
+size_t tc_workspace_held(tc_context *c) { return c->held; }
+size_t tc_workspace_share(tc_context *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    return tc_ws_share(c);
+}
+int tc_context_trim(tc_context *c)
+{
+    if (!c) return tc_fail(TC_ERR_VALUE, "null context");
+    TC_CUDA(cudaSetDevice(c->device));
+    TC_CUDA(cudaStreamSynchronize(c->stream));
+    tc_arena_free_all(c);
+    c->peak = 0;
+    return TC_OK;
+}
 
 int tc_alloc_pinned(size_t nbytes, void **out)
 {
@@ -204,13 +220,6 @@ static size_t st_workspace_per_plane(int64_t T, int64_t F, int64_t Fa, int nchun
     return N * 48 + pad * 9 + (size_t)T * F * 2 + (size_t)(T + F) * 8 + (1 << 16);
 }
 
-static size_t tc_workspace_budget()
-{
-    const char *e = getenv("TC_WORKSPACE_MB");
-    size_t mb = e ? (size_t)atoll(e) : 49152;
-    if (mb < 64) mb = 64;
-    return mb << 20;
-}
 
 static int st_validate(const tc_st_params *p)
 {
@@ -245,7 +254,7 @@ int tc_sum_threshold(tc_context *c, const tc_st_params *p, const void *vis, int 
     for (int k = 0; k < p->nwin_freq; k++) if (p->windows_freq[k] > maxw) maxw = p->windows_freq[k];
     size_t per_plane = st_workspace_per_plane(T, F, Fa, p->nchunk_ends - 1, maxw);
     size_t io_per_plane = (size_t)T * F * (2 + (space == TC_HOST ? esz + 1 : 0));
-    int64_t batch = (int64_t)(tc_workspace_budget() / (per_plane + io_per_plane));
+    int64_t batch = (int64_t)(tc_ws_share(c) / (per_plane + io_per_plane));
     if (batch < 1) batch = 1;
     if (batch > ncp) batch = ncp;
 
@@ -307,8 +316,9 @@ int tc_uvcontsub(tc_context *c, const void *vis, const uint8_t *flags, int64_t n
     for (int mi = 0; mi < major_cycles; mi++) {
         tc_prof_begin(c, TCP_UVCONTSUB);
         TC_CUDA(cudaMemsetAsync(unfl, 0, sizeof(int) * (size_t)ncp, c->stream));
-        TC_LAUNCH(k_uv_mean, dim3(tc_blocks_for(F, 256), (unsigned)ncp), 256, 0, c->stream, dvis, dout, (int)T,
-                  (int)F, avg, unfl);
+        for (int64_t p0 = 0; p0 < ncp; p0 += 65535)       // gridDim.y is limited to 65535
+            TC_LAUNCH(k_uv_mean, dim3(tc_blocks_for(F, 256), (unsigned)(ncp - p0 < 65535 ? ncp - p0 : 65535)), 256, 0,
+                      c->stream, dvis, dout, (int)T, (int)F, avg, unfl, p0);
         TC_LAUNCH(k_uv_smooth, (unsigned)ncp, 256, 0, c->stream, avg, tw, (int)F, K, smooth);
         // grid (channel pairs, dumps, planes): at most 65535 in y and z per launch
         for (int64_t p0 = 0; p0 < ncp; p0 += 65535)

@@ -91,6 +91,8 @@ def pack_data(time_inv, ubl,
     if slot.size and t[slot >= 0].size and (t[slot >= 0].min() < 0 or t[slot >= 0].max() >= ntime):
         raise ValueError("time_inv out of range")
     dev = _cabi.is_device_array(data)
+    if dev != _cabi.is_device_array(flags):
+        raise TypeError("tricolour_b200: data and flags must both be numpy arrays or both be CUDA tensors")
     if dev:
         import torch
         vis = data.contiguous()
@@ -203,3 +205,67 @@ def unpack_flags_equalised(antenna1, antenna2, time_inv, ubl, flag_windows):
         import torch
         return out.view(torch.bool)
     return out.view(np.bool_)
+
+
+# ---------------------------------------------------------------------------
+# block functions with the signatures of the reference's private per-block
+# functions; ``tricolour_b200.install()`` binds them over
+# ``tricolour.packing._fast_pack_data`` / ``_unpack_data`` (packing.py:281-292,
+# 391-415), which ``pack_data`` / ``unpack_data`` look up when dask runs a block
+# ---------------------------------------------------------------------------
+def _fast_pack_data(time_inv, ubl, ant1, ant2, data, flag, vis_windows, flag_windows):
+    """One row chunk scattered into the (shared, in-place) window objects
+    (packing.py:281-292 -> ``_numba_pack_data`` 243-278).  ``ubl`` arrives as
+    dask's nested list of baseline blocks, the windows as one-element lists.
+    The (row, chan, corr) -> (row, corr, chan) transposition runs on the GPU;
+    the host then copies whole channel runs into the windows."""
+    ubl = np.concatenate([bl for bl_list in ubl for bl in bl_list])
+    vis_win, flag_win = vis_windows[0], flag_windows[0]
+    data = np.asarray(data)
+    flag = np.asarray(flag)
+    rows, chans, corrs = data.shape
+    if vis_win.shape[3] != chans:
+        raise ValueError("channels mismatch")
+    if vis_win.shape[1] != corrs:
+        raise ValueError("correlations mismatch")
+    if vis_win.shape != flag_win.shape:
+        raise ValueError("vis_windows.shape != flag_windows.shape")
+    assert ubl.shape == (vis_win.shape[0], 3)
+    slot, t = _row_slots(ubl, ant1, ant2, time_inv, last_wins=True)
+    keep = np.flatnonzero(slot >= 0)
+    if keep.size:
+        # every row is its own "baseline" of one dump: the pack kernel then is the
+        # transposition of the chunk
+        ident = np.ascontiguousarray(np.arange(rows, dtype=np.int32))
+        zeros = np.zeros(rows, np.int32)
+        vis = np.ascontiguousarray(data, dtype=np.complex64)
+        fl8 = (np.ascontiguousarray(flag).view(np.uint8) if flag.dtype.itemsize == 1
+               else np.ascontiguousarray(flag != 0).view(np.uint8))
+        tv = np.empty((rows, corrs, 1, chans), np.complex64)
+        tf = np.empty((rows, corrs, 1, chans), np.uint8)
+        ctx, space = context_for(vis, fl8)
+        check(_cabi.load().tc_pack(ctx.handle, _hp(ident), _hp(zeros), rows, ptr(vis), ptr(fl8), chans, corrs,
+                                   1, rows, ptr(tv), ptr(tf), 1, space))
+        vis_win[slot[keep], :, t[keep], :] = tv[keep, :, 0, :]
+        flag_win[slot[keep], :, t[keep], :] = tf[keep, :, 0, :]
+    return np.array([[[True]]])
+
+
+def _unpack_data(antenna1, antenna2, time_inv, ubl, windows):
+    """All baseline chunks of a window gathered back into one row chunk
+    (packing.py:391-415).  ``ubl`` and ``windows`` are dask's lists of
+    one-element lists (one entry per baseline chunk)."""
+    exemplar = windows[0][0]
+    antenna1 = np.asarray(antenna1)
+    data = np.zeros((antenna1.shape[0], exemplar.shape[3], exemplar.shape[1]), dtype=exemplar.dtype)
+    for baselines, window in zip(ubl, windows):
+        baselines = np.asarray(baselines[0])
+        window = window[0]
+        u = baselines.copy()
+        u[:, 0] = u[:, 0] - u[:, 0].min()
+        slot, _ = _row_slots(u, antenna1, antenna2, time_inv, last_wins=False)
+        mine = slot >= 0
+        if not mine.any():
+            continue
+        data[mine] = unpack_data(antenna1, antenna2, time_inv, baselines, window)[mine]
+    return data

@@ -99,6 +99,11 @@ class StrategyExecutor(object):
         reference overlaps its I/O with flagging the same way (app.py:266-271).
         Device and page-locked staging buffers for ``depth`` + 1 blocks are kept
         on the executor and reused.
+
+        Buffer reuse: the arrays of a block are read until the iterator is asked
+        for the following block (the executor waits for the block's upload before
+        it calls ``next``), so a generator may refill one pair of page-locked
+        buffers in place for every block it yields.
         """
         import torch
         if not torch.cuda.is_available():
@@ -191,11 +196,18 @@ class StrategyExecutor(object):
                 # a slot's page-locked output must have been consumed before its reuse
                 while len(pending) >= nslots - 1:
                     yield pending.pop(0).result()
+                slot, ev_up, fdt, _src = cur
+                # The copy of the block just taken from the iterator reads the caller's arrays
+                # asynchronously.  The iterator may refill those very buffers as soon as it is
+                # asked for the next block (one page-locked buffer per stream of blocks is the
+                # usage INTEGRATION.md recommends), so the copy must have finished first.  It was
+                # queued one whole block of flagging ago: this wait is normally free.
+                ev_up.synchronize()
+                _src = None
                 try:
                     nxt = upload(next(it), k)      # queued before this block's kernels: overlaps them
                 except StopIteration:
                     nxt = None
-                slot, ev_up, fdt, _src = cur
                 prep = copier.submit(prepare, tuple(pipe["f"][slot].shape))
                 main.wait_event(ev_up)
                 if trace is not None:

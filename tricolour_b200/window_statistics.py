@@ -6,7 +6,8 @@ The counting (per baseline and per channel sums of the flag bytes) is one GPU
 reduction; the dictionary bookkeeping, the channel-bin edges and the text
 summary stay in Python exactly like the reference.  ``allreduce_window_stats``
 adds the one collective of the multi-GPU path: a single small all-reduce of the
-packed count vector (NCCL over NVLink on GPUs, gloo in CPU tests).
+count vector in the fixed layout of ``StatsLayout`` (NCCL over NVLink on GPUs,
+gloo in CPU tests).
 """
 import ctypes
 from collections import defaultdict
@@ -19,41 +20,38 @@ from ._cabi import check, ptr, context_for
 from .packing import _WINDOW_SCHEMA  # noqa: F401
 
 
+_SCALAR_TABLES = tuple("_%s_per_%s" % (kind, what) for what in ("ant", "field", "scan", "bl")
+                       for kind in ("counts", "size")) + ("_size_per_ddid",)
+
+
 class WindowStatistics(object):
-    """Accumulator with the reference's fields (window_statistics.py:173-231)."""
+    """Flag-count accumulator with the attribute names of the reference's class
+    (window_statistics.py:173-231), which its ``summarise_stats`` and the
+    application read: ``_counts_per_{ant,field,scan,bl}``, ``_size_per_*``,
+    ``_counts_per_ddid`` (``nchanbins`` uint64 bins per data descriptor),
+    ``_bins_per_ddid`` (bin frequency labels) and ``_size_per_ddid``."""
 
     def __init__(self, nchanbins):
         self._nchanbins = nchanbins
-        self._counts_per_ant = defaultdict(lambda: 0)
-        self._counts_per_field = defaultdict(lambda: 0)
-        self._counts_per_scan = defaultdict(lambda: 0)
-        self._counts_per_bl = defaultdict(lambda: 0)
-        self._size_per_ant = defaultdict(lambda: 0)
-        self._size_per_field = defaultdict(lambda: 0)
-        self._size_per_scan = defaultdict(lambda: 0)
-        self._size_per_bl = defaultdict(lambda: 0)
-        bin_factory = partial(np.zeros, nchanbins, dtype=np.uint64)
-        self._counts_per_ddid = defaultdict(bin_factory)
-        self._bins_per_ddid = defaultdict(lambda: 0)
-        self._size_per_ddid = defaultdict(lambda: 0)
+        for table in _SCALAR_TABLES:
+            setattr(self, table, defaultdict(int))
+        self._counts_per_ddid = defaultdict(partial(np.zeros, nchanbins, dtype=np.uint64))
+        self._bins_per_ddid = defaultdict(int)
 
     def update(self, other):
-        for name in ("_counts_per_ant", "_counts_per_field", "_counts_per_scan",
-                     "_counts_per_bl", "_size_per_ant", "_size_per_field",
-                     "_size_per_scan", "_size_per_ddid", "_size_per_bl"):
-            mine = getattr(self, name)
-            for k, v in getattr(other, name).items():
-                mine[k] += v
-        for d, count in other._counts_per_ddid.items():
-            self._counts_per_ddid[d] += count
-        for d, bins in other._bins_per_ddid.items():
-            self._bins_per_ddid[d] = bins  # frequency labels
+        """adds ``other`` into this accumulator (the frequency labels are copied)"""
+        for table in _SCALAR_TABLES:
+            mine, theirs = getattr(self, table), getattr(other, table)
+            for key, value in theirs.items():
+                mine[key] += value
+        for ddid, bins in other._counts_per_ddid.items():
+            self._counts_per_ddid[ddid] += bins
+        self._bins_per_ddid.update(other._bins_per_ddid)
 
     def copy(self):
-        """ Creates a copy of the current WindowStatistics"""
-        result = WindowStatistics(self._nchanbins)
-        result.update(self)
-        return result
+        out = WindowStatistics(self._nchanbins)
+        out.update(self)
+        return out
 
 
 def _counts(flag_window):
@@ -152,107 +150,143 @@ def combine_window_stats(window_stats):
     return result
 
 
-def allreduce_window_stats(stats, group=None, device=None):
-    """Sums a :class:`WindowStatistics` over all ranks of ``torch.distributed``:
-    every dictionary is packed into one int64 vector (keys are exchanged once
-    with ``all_gather_object``) and reduced with a single ``all_reduce``."""
+class StatsLayout(object):
+    """Fixed layout of a :class:`WindowStatistics` as one int64 vector
+    (SURVEY.md 8(e)): ``[per-antenna counts, per-antenna sizes, per-baseline counts
+    (all baselines of the observation, zero where a rank owns none of a baseline),
+    per-baseline sizes, per-field count+size, per-scan count+size, per-ddid
+    channel-bin counts, per-ddid size]``.  Every rank builds the same layout from
+    observation metadata (antenna names, the global ``ubl`` table, field names,
+    scan numbers, the channel frequencies of every data descriptor), so no keys
+    have to be exchanged and the statistics of all ranks are summed by ONE
+    all-reduce.  It replaces the host-side ``combine_window_stats`` of the
+    reference (window_statistics.py:143-170) across processes."""
+
+    def __init__(self, antenna_names, ubl, field_names, scan_numbers, ddid_chan_freqs, nchanbins=10):
+        self.antenna_names = list(antenna_names)
+        ubl = np.asarray(ubl)
+        self.bl_names = []
+        for a1, a2 in ubl[:, 1:3]:
+            name = "{0:s}&{1:s}".format(self.antenna_names[int(a1)], self.antenna_names[int(a2)])
+            if name not in self.bl_names:
+                self.bl_names.append(name)
+        self.field_names = list(field_names)
+        self.scan_numbers = list(scan_numbers)
+        self.ddids = list(ddid_chan_freqs.keys())
+        self.nchanbins = int(nchanbins)
+        # channel-bin labels exactly as _window_stats computes them (window_statistics.py:53-55)
+        self.bin_edges = {d: np.linspace(np.min(f), np.max(f), self.nchanbins)
+                          for d, f in ddid_chan_freqs.items()}
+        self._fields = (("_counts_per_ant", self.antenna_names), ("_size_per_ant", self.antenna_names),
+                        ("_counts_per_bl", self.bl_names), ("_size_per_bl", self.bl_names),
+                        ("_counts_per_field", self.field_names), ("_size_per_field", self.field_names),
+                        ("_counts_per_scan", self.scan_numbers), ("_size_per_scan", self.scan_numbers),
+                        ("_size_per_ddid", self.ddids))
+        self.size = sum(len(k) for _, k in self._fields) + len(self.ddids) * self.nchanbins
+
+    def pack(self, stats):
+        """int64 vector of ``stats``; a key outside the layout is an error (it
+        would silently vanish from the reduced statistics)"""
+        if stats._nchanbins != self.nchanbins:
+            raise ValueError("statistics have %d channel bins, the layout %d" % (stats._nchanbins, self.nchanbins))
+        vec = np.zeros(self.size, np.int64)
+        pos = 0
+        for name, keys in self._fields:
+            d = getattr(stats, name)
+            extra = set(d.keys()) - set(keys)
+            if extra:
+                raise ValueError("%s holds keys outside the layout: %s" % (name, sorted(map(str, extra))[:4]))
+            for k in keys:
+                if k in d:
+                    vec[pos] = int(d[k])
+                pos += 1
+        extra = set(stats._counts_per_ddid.keys()) - set(self.ddids)
+        if extra:
+            raise ValueError("_counts_per_ddid holds keys outside the layout: %s" % sorted(extra)[:4])
+        for k in self.ddids:
+            if k in stats._counts_per_ddid:
+                vec[pos:pos + self.nchanbins] = np.asarray(stats._counts_per_ddid[k]).astype(np.int64)
+            pos += self.nchanbins
+        return vec
+
+    def unpack(self, vec):
+        """:class:`WindowStatistics` from a (reduced) vector; keys whose size is
+        zero everywhere (nothing was counted for them) are left out, like in the
+        reference where a key only exists once a block contributed to it"""
+        vec = np.asarray(vec).astype(np.int64)
+        out = WindowStatistics(self.nchanbins)
+        pos = 0
+        vals = {}
+        for name, keys in self._fields:
+            vals[name] = vec[pos:pos + len(keys)]
+            pos += len(keys)
+        pairs = (("_counts_per_ant", "_size_per_ant", self.antenna_names),
+                 ("_counts_per_bl", "_size_per_bl", self.bl_names),
+                 ("_counts_per_field", "_size_per_field", self.field_names),
+                 ("_counts_per_scan", "_size_per_scan", self.scan_numbers))
+        for cn, sn, keys in pairs:
+            for i, k in enumerate(keys):
+                if vals[sn][i] != 0 or vals[cn][i] != 0:
+                    getattr(out, cn)[k] += int(vals[cn][i])
+                    getattr(out, sn)[k] += int(vals[sn][i])
+        for i, k in enumerate(self.ddids):
+            bins = vec[pos:pos + self.nchanbins]
+            pos += self.nchanbins
+            if vals["_size_per_ddid"][i] != 0 or bins.any():
+                out._size_per_ddid[k] += int(vals["_size_per_ddid"][i])
+                out._counts_per_ddid[k] += bins.astype(np.uint64)
+                out._bins_per_ddid[k] = self.bin_edges[k]
+        return out
+
+
+def allreduce_window_stats(stats, layout=None, group=None, device=None):
+    """Sums a :class:`WindowStatistics` over all ranks of ``torch.distributed``
+    with exactly ONE collective: the statistics are packed into the fixed int64
+    layout of :class:`StatsLayout` and reduced by a single ``all_reduce`` (NCCL
+    over NVLink on GPUs, gloo in the CPU tests).  ``stats`` may also be a
+    sequence of statistics (e.g. ``(original, final)``): they share the one
+    all-reduce and a tuple is returned.  Without a process group (or with one
+    rank) copies are returned and nothing is communicated."""
     import torch
     import torch.distributed as dist
+    many = isinstance(stats, (list, tuple))
+    items = list(stats) if many else [stats]
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return stats.copy()
-    names = ("_counts_per_ant", "_counts_per_field", "_counts_per_scan", "_counts_per_bl",
-             "_size_per_ant", "_size_per_field", "_size_per_scan", "_size_per_bl",
-             "_size_per_ddid")
-    local_keys = {n: list(getattr(stats, n).keys()) for n in names}
-    local_keys["_ddid"] = list(stats._counts_per_ddid.keys())
-    gathered = [None] * dist.get_world_size(group)
-    dist.all_gather_object(gathered, local_keys, group=group)
-    keys = {}
-    for n in list(names) + ["_ddid"]:
-        seen = []
-        for g in gathered:
-            for k in g[n]:
-                if k not in seen:
-                    seen.append(k)
-        keys[n] = seen
-    vec = []
-    for n in names:
-        d = getattr(stats, n)
-        vec.extend(int(d[k]) if k in d else 0 for k in keys[n])
-    nb = stats._nchanbins
-    for k in keys["_ddid"]:
-        if k in stats._counts_per_ddid:
-            vec.extend(int(x) for x in stats._counts_per_ddid[k])
-        else:
-            vec.extend([0] * nb)
+        outs = [s.copy() for s in items]
+        return tuple(outs) if many else outs[0]
+    if layout is None:
+        raise ValueError("allreduce_window_stats needs a StatsLayout when more than one rank takes part: "
+                         "the vector layout must be identical on every rank without exchanging keys")
+    vec = np.concatenate([layout.pack(s) for s in items])
     backend = dist.get_backend(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    t = torch.tensor(vec, dtype=torch.int64, device=device)
+    t = torch.from_numpy(vec).to(device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    vals = t.cpu().tolist()
-    out = WindowStatistics(nb)
-    pos = 0
-    for n in names:
-        d = getattr(out, n)
-        for k in keys[n]:
-            d[k] += vals[pos]
-            pos += 1
-    for k in keys["_ddid"]:
-        out._counts_per_ddid[k] += np.array(vals[pos:pos + nb], dtype=np.uint64)
-        pos += nb
-    # frequency labels are identical on every rank that has them
-    bins = [None] * dist.get_world_size(group)
-    dist.all_gather_object(bins, {k: np.asarray(v).tolist() for k, v in stats._bins_per_ddid.items()},
-                           group=group)
-    for b in bins:
-        for k, v in b.items():
-            out._bins_per_ddid[k] = np.asarray(v)
-    return out
+    vals = t.cpu().numpy()
+    outs = [layout.unpack(vals[i * layout.size:(i + 1) * layout.size]) for i in range(len(items))]
+    return tuple(outs) if many else outs[0]
 
 
 def summarise_stats(final, original):
-    """
-    Returns a list of strings summarising final and original flag percentages
-    (window_statistics.py:234-294).
-    """
-    l = []  # noqa
-    l.append("********************************")
-    l.append("   BEGINNING OF FLAG SUMMARY    ")
-    l.append("********************************")
-
-    def pct(cnt, size):
-        return cnt * 100.0 / size
-
-    l.append("Per antenna:")
-    for a in final._counts_per_ant:
-        l.append("\t {0:s}: {1:.3f}%, original {2:.3f}%".format(
-            a, pct(final._counts_per_ant[a], final._size_per_ant[a]),
-            pct(original._counts_per_ant[a], original._size_per_ant[a])))
-    l.append("Per scan:")
-    for s in final._counts_per_scan:
-        l.append("\t {0:d}: {1:.3f}%, original {2:.3f}%".format(
-            s, pct(final._counts_per_scan[s], final._size_per_scan[s]),
-            pct(original._counts_per_scan[s], original._size_per_scan[s])))
-    l.append("Per field:")
-    for f in final._counts_per_field:
-        l.append("\t {0:s}: {1:.3f}%, original {2:.3f}%".format(
-            f, pct(final._counts_per_field[f], final._size_per_field[f]),
-            pct(original._counts_per_field[f], original._size_per_field[f])))
-    l.append("Per baseline:")
-    for b in final._counts_per_bl:
-        l.append("\t {0:s}: {1:.3f}%, original {2:.3f}%".format(
-            b, pct(final._counts_per_bl[b], final._size_per_bl[b]),
-            pct(original._counts_per_bl[b], original._size_per_bl[b])))
-    l.append("Per data descriptor id:")
-    for d in final._counts_per_ddid:
-        ratios = final._counts_per_ddid[d] * 100.0 / final._size_per_ddid[d]
-        ratio_str = '\t'.join(["{0:<7.2f}".format(r) for r in ratios])
-        l.append("\t {0:d}: {1:s}%".format(d, ratio_str))
-        ddid_freqs = final._bins_per_ddid[d] / 1e6
-        ddid_freqs_str = '\t'.join(["{0:<7.1f}".format(f) for f in ddid_freqs])
-        l.append("\t    {0:s} MHz".format(ddid_freqs_str))
-    l.append("********************************")
-    l.append("       END OF FLAG SUMMARY      ")
-    l.append("********************************")
-    return l
+    """The text summary of final against original flag percentages, line for
+    line what the reference logs (window_statistics.py:234-294)."""
+    stars = "*" * 32
+    lines = [stars, "   BEGINNING OF FLAG SUMMARY    ", stars]
+    sections = (("Per antenna:", "ant", "{0:s}"), ("Per scan:", "scan", "{0:d}"),
+                ("Per field:", "field", "{0:s}"), ("Per baseline:", "bl", "{0:s}"))
+    for title, what, keyfmt in sections:
+        lines.append(title)
+        fc, fs = getattr(final, "_counts_per_" + what), getattr(final, "_size_per_" + what)
+        oc, os_ = getattr(original, "_counts_per_" + what), getattr(original, "_size_per_" + what)
+        for key in fc:
+            lines.append(("\t " + keyfmt + ": {1:.3f}%, original {2:.3f}%").format(
+                key, fc[key] * 100.0 / fs[key], oc[key] * 100.0 / os_[key]))
+    lines.append("Per data descriptor id:")
+    for ddid in final._counts_per_ddid:
+        ratios = final._counts_per_ddid[ddid] * 100.0 / final._size_per_ddid[ddid]
+        lines.append("\t {0:d}: {1:s}%".format(ddid, '\t'.join("{0:<7.2f}".format(r) for r in ratios)))
+        mhz = final._bins_per_ddid[ddid] / 1e6
+        lines.append("\t    {0:s} MHz".format('\t'.join("{0:<7.1f}".format(f) for f in mhz)))
+    lines += [stars, "       END OF FLAG SUMMARY      ", stars]
+    return lines

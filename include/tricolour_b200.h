@@ -174,6 +174,23 @@ int tc_unpack_flags_any_corr(tc_context *ctx, const int32_t *row_bl, const int32
                              int64_t nrow, const uint8_t *window, int64_t nchan,
                              int64_t ncorr, int64_t ntime, int64_t nbl, uint8_t *out,
                              int space);
+/* the same gather with the any(corr) result broadcast over ncorr_out correlations: a
+ * one-correlation window (polarised / total-power flagging, app.py:415-432) goes back to
+ * rows of the measurement set's correlation count (app.py:479-480 broadcast_to). */
+int tc_unpack_flags_broadcast(tc_context *ctx, const int32_t *row_bl, const int32_t *row_t,
+                              int64_t nrow, const uint8_t *window, int64_t nchan,
+                              int64_t ncorr_win, int64_t ncorr_out, int64_t ntime,
+                              int64_t nbl, uint8_t *out, int space);
+/* polarised_intensity (stokes.py:157-209; unpolarised 79-154 when nunpol > 0),
+ * flags.any(axis=2) (app.py:420, 432) and _numba_pack_data (packing.py:243-278) in one
+ * pass over the rows: vis/flags (row, chan, ncorr) -> windows (nbl, 1, ntime, nchan).
+ * Terms as for tc_polarised_intensity; fill as for tc_pack. */
+int tc_stokes_pack(tc_context *ctx, const int32_t *row_bl, const int32_t *row_t, int64_t nrow,
+                   const void *vis_c64, const uint8_t *flags, int64_t nchan, int64_t ncorr,
+                   int64_t ntime, int64_t nbl, const int32_t *unpol_idx,
+                   const double *unpol_coef, int nunpol, const int32_t *pol_idx,
+                   const double *pol_coef, int npol, void *vis_win, uint8_t *flag_win,
+                   int fill, int space);
 
 /* ---- W1: window statistics, tricolour/window_statistics.py:12-66 -------- */
 /* bl_counts[nbl], chan_counts[nchan]: sums of the flag bytes, always returned

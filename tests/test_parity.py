@@ -593,6 +593,72 @@ def test_pack_unpack_roundtrip(backend, nchan):
         tb.unique_baselines(A1.astype(np.int64), A2)
 
 
+@pytest.mark.parametrize("nchan,ncorr", [(32, 4), (48, 2), (21, 4)])
+def test_polarised_pack_and_broadcast_unpack(backend, nchan, ncorr):
+    """N2: Stokes + any(corr) fused into the pack (app.py:415-432 + packing.py:243-278)
+    and the one-correlation window broadcast back to row order (app.py:479-480)"""
+    rs = np.random.RandomState(17)
+    na, ntime = 5, 9
+    a1, a2 = (a.astype(np.int32) for a in np.triu_indices(na, 0))
+    nbl = a1.size
+    A1, A2 = np.tile(a1, ntime), np.tile(a2, ntime)
+    tinv = np.repeat(np.arange(ntime), nbl)
+    keep = np.ones(A1.size, bool)
+    keep[rs.choice(A1.size, 11, replace=False)] = False
+    A1, A2, tinv = A1[keep], A2[keep], tinv[keep]
+    nrow = A1.size
+    vis = (rs.standard_normal((nrow, nchan, ncorr)) + 1j * rs.standard_normal((nrow, nchan, ncorr))).astype(np.complex64)
+    flag = rs.uniform(size=(nrow, nchan, ncorr)) < 0.1
+    ubl = tb.unique_baselines(A1, A2).view(np.int32).reshape(-1, 2)
+    ubl = np.concatenate([np.arange(ubl.shape[0], dtype=np.int32)[:, None], ubl], axis=1)
+    if ncorr == 4:
+        smap = tb.stokes_corr_map([9, 10, 11, 12])
+    else:
+        smap = tb.stokes_corr_map([9, 12])
+    pol = tuple(v for k, v in smap.items() if k != 'I')
+    unpol = tuple(v for k, v in smap.items() if k == 'I')
+    vw, fw = tb.packing.pack_polarised(tinv, ubl, A1, A2, vis, flag, ntime, pol)
+    pi = oracle.polarised_intensity(vis, pol)
+    vw2, fw2 = oracle.pack_data(tinv, ubl, A1, A2, pi, flag.any(axis=2, keepdims=True), ntime)
+    assert vw.shape == (nbl, 1, ntime, nchan)
+    assert_same(vw, vw2, "polarised pack vis")
+    assert_same(fw, fw2, "polarised pack flags")
+    vw, fw = tb.packing.pack_polarised(tinv, ubl, A1, A2, vis, flag, ntime, pol, unpol)
+    ui = oracle.unpolarised_intensity(vis, unpol, pol)
+    vw2, _ = oracle.pack_data(tinv, ubl, A1, A2, ui, flag.any(axis=2, keepdims=True), ntime)
+    assert_same(vw, vw2, "unpolarised pack vis")
+    # flag the window some more, then back to rows of ncorr correlations
+    fw = fw | (rs.uniform(size=fw.shape) < 0.2)
+    got = tb.packing.unpack_flags_equalised(A1, A2, tinv, ubl, fw, ncorr_out=ncorr)
+    want = np.broadcast_to(oracle.unpack_data(A1, A2, tinv, ubl, fw), (nrow, nchan, ncorr))
+    assert got.shape == (nrow, nchan, ncorr)
+    assert_same(got, want, "broadcast unpack")
+    # uint8 windows holding values other than 0/1 still come back as booleans
+    got8 = tb.packing.unpack_flags_equalised(A1, A2, tinv, ubl, fw.astype(np.uint8) * 7, ncorr_out=ncorr)
+    assert_same(got8, want)
+    with pytest.raises(ValueError):
+        tb.packing.pack_polarised(tinv, ubl, A1, A2, vis, flag, ntime, ())
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 70, 64), (3, 2, 300, 48), (2, 1, 7, 4112), (4, 4, 9, 20)])
+def test_window_counts_shapes(backend, shape):
+    """the 16-byte counting kernel (F % 16 == 0; more rows than one 256-row segment;
+    more than one 4096-channel tile) and the general one, bool and valued uint8 windows"""
+    rs = np.random.RandomState(sum(shape))
+    nbl, ncorr, T, F = shape
+    ubl = common.baselines(8)[:nbl]
+    cf, _ = common.channels(F)
+    names = ["m%03d" % i for i in range(8)]
+    for fw in (rs.uniform(size=shape) < 0.3, (rs.uniform(size=shape) < 0.3).astype(np.uint8) * rs.randint(1, 256, shape).astype(np.uint8)):
+        blc, chc = tb.window_statistics._counts(fw)
+        assert blc.tolist() == fw.reshape(nbl, -1).sum(axis=1, dtype=np.uint64).tolist()
+        assert chc.tolist() == fw.sum(axis=(0, 1, 2), dtype=np.uint64).tolist()
+        st = tb.window_stats(fw, ubl, cf, names, 0, "f", 0)
+        want = oracle.window_counts(fw, ubl, cf, 8)
+        assert [int(st._counts_per_ant[n]) for n in names] == [int(x) for x in want[0]]
+        assert np.array_equal(st._counts_per_ddid[0], want[6].astype(np.uint64))
+
+
 def test_window_stats(backend):
     g = golden("packing.npz")
     ubl, fw, cf = g["ubl"], g["flag_win"], g["chan_freqs"]

@@ -86,6 +86,9 @@ _SIGNATURES = {
     "tc_pack": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _int]),
     "tc_unpack": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int]),
     "tc_unpack_flags_any_corr": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int]),
+    "tc_unpack_flags_broadcast": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _int]),
+    "tc_stokes_pack": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp, _int,
+                              _vp, _vp, _int, _int]),
     "tc_window_counts": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int]),
     "tc_flags_or": (_int, [_vp, _vp, _vp, _vp, _i64, _int]),
     "tc_stage_average_freq": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int]),

@@ -237,6 +237,24 @@ __device__ __forceinline__ double stokes_abs(const float2 *v, const StokesTerms 
     return tc_hypot(vr, vi);
 }
 
+// sqrt(sum |pol term|^2), or (sum |unpol term|) - that, in float64 (stokes.py:132-153, 196-208)
+__device__ __forceinline__ double stokes_intensity(const float2 *v, const StokesTerms &pol, const StokesTerms &unpol,
+                                                   int with_unpol)
+{
+    double p = 0.0;
+    for (int k = 0; k < pol.n; k++) {
+        double a = stokes_abs(v, pol, k);
+        p = __dadd_rn(p, __dmul_rn(a, a));
+    }
+    double r = __dsqrt_rn(p);
+    if (with_unpol) {
+        double u = 0.0;
+        for (int k = 0; k < unpol.n; k++) u = __dadd_rn(u, stokes_abs(v, unpol, k));
+        r = __dadd_rn(u, -r);
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 k_stokes(const float2 *__restrict__ vis, int64_t n, int ncorr, StokesTerms pol,
          StokesTerms unpol, int with_unpol, float2 *__restrict__ out)
@@ -252,18 +270,7 @@ k_stokes(const float2 *__restrict__ vis, int64_t n, int ncorr, StokesTerms pol,
     } else {
         for (int c = 0; c < ncorr && c < 8; c++) v[c] = src[c];
     }
-    double p = 0.0;
-    for (int k = 0; k < pol.n; k++) {
-        double a = stokes_abs(v, pol, k);
-        p = __dadd_rn(p, __dmul_rn(a, a));
-    }
-    double r = __dsqrt_rn(p);
-    if (with_unpol) {
-        double u = 0.0;
-        for (int k = 0; k < unpol.n; k++) u = __dadd_rn(u, stokes_abs(v, unpol, k));
-        r = __dadd_rn(u, -r);
-    }
-    out[i] = make_float2((float)r, 0.0f);
+    out[i] = make_float2((float)stokes_intensity(v, pol, unpol, with_unpol), 0.0f);
 }
 
 // ----------------------------------------------------------------------------

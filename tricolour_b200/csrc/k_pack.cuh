@@ -9,6 +9,7 @@
 // writes are ncorr streams that are each contiguous across the warp.
 #pragma once
 #include "tc_common.cuh"
+#include "k_elementwise.cuh"
 
 // window defaults (packing.py:96-98, 116-117): vis = NaN + NaNj, flag = 1
 __global__ void __launch_bounds__(256)
@@ -86,7 +87,7 @@ k_pack_c4(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t,
 }
 
 // gather back; ELEM is float2 (vis) or u8 (flags).  Rows without a window slot
-// stay zero (packing.py:396).
+// stay zero (packing.py:396).  General form (any ncorr): one thread per (row, chan).
 template <typename ELEM>
 __global__ void __launch_bounds__(256)
 k_unpack(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
@@ -107,11 +108,105 @@ k_unpack(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, 
     }
 }
 
-// flags only: out[r, f, :] = any over corr (app.py:479-480 fused into the gather)
+// ncorr == 4 flags: a thread gathers 4 channels of the 4 correlation rows as four
+// 32-bit words (each window row read is contiguous across the warp), transposes the
+// 4 x 4 bytes in registers and writes the 16 row-order bytes with one store.
+//   MODE 0: plain gather                        (packing.py:369-415)
+//   MODE 1: any(corr) broadcast over the 4 correlations (app.py:479-480)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_unpack_flags_c4(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
+                  const uint32_t *__restrict__ win, int nchan4, int ntime, uint4 *__restrict__ out)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nrow * nchan4) return;
+    const int64_t r = g / nchan4;
+    const int f4 = (int)(g - r * nchan4);
+    const int bl = row_bl[r];
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (bl >= 0) {
+        const int t = row_t[r];
+        uint32_t w[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) w[c] = win[(((int64_t)bl * 4 + c) * ntime + t) * nchan4 + f4];
+        if (MODE == 1) {
+            uint32_t any = w[0] | w[1] | w[2] | w[3];
+            // bytes -> 0/1, then every channel's byte replicated over the 4 correlations
+            any = (any | (any >> 4)) & 0x0f0f0f0fu;
+            any = (any | (any >> 2)) & 0x03030303u;
+            any = (any | (any >> 1)) & 0x01010101u;
+            o.x = (any & 0xffu) * 0x01010101u;
+            o.y = ((any >> 8) & 0xffu) * 0x01010101u;
+            o.z = ((any >> 16) & 0xffu) * 0x01010101u;
+            o.w = (any >> 24) * 0x01010101u;
+        } else {
+            // out word k (channel k) = bytes k of w[0..3]
+            o.x = (w[0] & 0xffu) | ((w[1] & 0xffu) << 8) | ((w[2] & 0xffu) << 16) | ((w[3] & 0xffu) << 24);
+            o.y = ((w[0] >> 8) & 0xffu) | (((w[1] >> 8) & 0xffu) << 8) | (((w[2] >> 8) & 0xffu) << 16) |
+                  (((w[3] >> 8) & 0xffu) << 24);
+            o.z = ((w[0] >> 16) & 0xffu) | (((w[1] >> 16) & 0xffu) << 8) | (((w[2] >> 16) & 0xffu) << 16) |
+                  (((w[3] >> 16) & 0xffu) << 24);
+            o.w = (w[0] >> 24) | ((w[1] >> 24) << 8) | ((w[2] >> 24) << 16) | ((w[3] >> 24) << 24);
+        }
+    }
+    out[g] = o;
+}
+
+// one-correlation window (polarised flagging, app.py:415-432) back to rows of NOUT = 4
+// correlations: 16 channels per thread (one 16-byte window read), every flag byte
+// normalised to 0/1 and replicated over the correlations (four 16-byte stores)
+__global__ void __launch_bounds__(256)
+k_unpack_flags_c1_to4(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
+                      const uint4 *__restrict__ win, int nchan16, int ntime, uint4 *__restrict__ out)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nrow * nchan16) return;
+    const int64_t r = g / nchan16;
+    const int f16 = (int)(g - r * nchan16);
+    const int bl = row_bl[r];
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (bl >= 0) w = win[((int64_t)bl * ntime + row_t[r]) * nchan16 + f16];
+    const uint32_t in[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t any = in[k];
+        any = (any | (any >> 4)) & 0x0f0f0f0fu;
+        any = (any | (any >> 2)) & 0x03030303u;
+        any = (any | (any >> 1)) & 0x01010101u;
+        out[g * 4 + k] = make_uint4((any & 0xffu) * 0x01010101u, ((any >> 8) & 0xffu) * 0x01010101u,
+                                    ((any >> 16) & 0xffu) * 0x01010101u, (any >> 24) * 0x01010101u);
+    }
+}
+
+// ncorr == 4 visibilities: a thread gathers one channel of the 4 correlation rows
+// (8-byte reads, contiguous across the warp per row) and writes its 32 row-order bytes
+__global__ void __launch_bounds__(256)
+k_unpack_vis_c4(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
+                const float2 *__restrict__ win, int nchan, int ntime, float4 *__restrict__ out)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nrow * nchan) return;
+    const int64_t r = g / nchan;
+    const int f = (int)(g - r * nchan);
+    const int bl = row_bl[r];
+    float2 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = make_float2(0.f, 0.f);
+    if (bl >= 0) {
+        const int t = row_t[r];
+#pragma unroll
+        for (int c = 0; c < 4; c++) v[c] = win[(((int64_t)bl * 4 + c) * ntime + t) * nchan + f];
+    }
+    out[g * 2] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    out[g * 2 + 1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+
+// flags only, any ncorr_win -> ncorr_out: out[r, f, :] = any over the window's
+// correlations (app.py:479-480 fused into the gather); general fallback
 __global__ void __launch_bounds__(256)
 k_unpack_any_corr(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t,
                   int64_t nrow, const u8 *__restrict__ win, int nchan, int ncorr, int ntime,
-                  u8 *__restrict__ out)
+                  int ncorr_out, u8 *__restrict__ out)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nrow * nchan) return;
@@ -123,12 +218,50 @@ k_unpack_any_corr(const int32_t *__restrict__ row_bl, const int32_t *__restrict_
     if (bl >= 0)
         for (int c = 0; c < ncorr; c++) any |= win[(((int64_t)bl * ncorr + c) * ntime + t) * nchan + f];
     any = any ? 1 : 0;
-    for (int c = 0; c < ncorr; c++) out[g * ncorr + c] = any;
+    for (int c = 0; c < ncorr_out; c++) out[g * ncorr_out + c] = any;
 }
 
-// W1: sums of the flag bytes per baseline and per channel.  grid = (segments,
-// nbl); a block walks `rows_per_seg` window rows of one baseline, every thread
-// owning a strided set of channels, then folds with warp shuffles.
+// ----------------------------------------------------------------------------
+// K2 + N2 + P1 fused (polarised / total-power flagging, app.py:415-432 followed by
+// pack_data): per (row, chan) the Stokes intensity of the correlations
+// (stokes.py:157-209, or 79-154 with `with_unpol`) and the OR of their flags go
+// straight into the one-correlation windows (nbl, 1, T, F).  The rows are read once
+// (32 + 4 bytes per sample for 4 correlations), 9 bytes are written.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stokes_pack(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
+              const float2 *__restrict__ vis, const u8 *__restrict__ flags, int nchan, int ncorr, int ntime,
+              StokesTerms pol, StokesTerms unpol, int with_unpol, float2 *__restrict__ vis_win,
+              u8 *__restrict__ flag_win)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nrow * nchan) return;
+    const int64_t r = g / nchan;
+    const int f = (int)(g - r * nchan);
+    const int bl = row_bl[r];
+    if (bl < 0) return;
+    const int t = row_t[r];
+    float2 v[8];
+    const float2 *src = vis + g * ncorr;
+    u8 any = 0;
+    if (ncorr == 4 && (((uintptr_t)src) & 15) == 0 && (((uintptr_t)(flags + g * 4)) & 3) == 0) {
+        const float4 a = ((const float4 *)src)[0], b = ((const float4 *)src)[1];
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+        any = *reinterpret_cast<const uint32_t *>(flags + g * 4) ? 1 : 0;
+    } else {
+        for (int c = 0; c < ncorr && c < 8; c++) { v[c] = src[c]; any |= flags[g * ncorr + c]; }
+        any = any ? 1 : 0;
+    }
+    const int64_t dst = ((int64_t)bl * ntime + t) * nchan + f;
+    vis_win[dst] = make_float2((float)stokes_intensity(v, pol, unpol, with_unpol), 0.0f);
+    flag_win[dst] = any;
+}
+
+// W1: sums of the flag bytes per baseline and per channel (window_statistics.py:
+// 26-64 sums the flag array itself, so a uint8 window contributes its byte values).
+// General form: grid = (segments, nbl); a block walks `rows_per_seg` window rows of one
+// baseline, every thread owning a strided set of channels, then folds with warp shuffles.
 __global__ void __launch_bounds__(256)
 k_window_counts(const u8 *__restrict__ flags, int64_t rows_per_bl, int rows_per_seg, int F,
                 unsigned long long *__restrict__ bl_counts, unsigned long long *__restrict__ chan_counts)
@@ -150,4 +283,98 @@ k_window_counts(const u8 *__restrict__ flags, int64_t rows_per_bl, int rows_per_
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_tot, mine);
     __syncthreads();
     if (threadIdx.x == 0 && s_tot) atomicAdd(&bl_counts[bl], s_tot);
+}
+
+// Vector form (F % 16 == 0): a thread owns 16 adjacent channels, a block of 256 threads a
+// tile of 4096 channels, and walks up to 256 window rows of one baseline with one 16-byte
+// load per row: every row is read fully coalesced.  The 16 column sums of a thread live in
+// eight registers as packed 16-bit fields (256 rows x 255 cannot overflow them).  A block
+// leaves its column sums in its own slice of `partial` (plain stores, no atomics) and adds
+// its total to the baseline with ONE atomic; k_window_counts_fold sums the slices.
+#define TC_WC_ROWS 256
+__global__ void __launch_bounds__(256)
+k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, uint32_t *__restrict__ partial,
+                    unsigned long long *__restrict__ bl_counts)
+{
+    __shared__ unsigned s_tot[8];
+    const int seg = blockIdx.x, tile = blockIdx.y;
+    const int64_t bl = blockIdx.z;
+    const int f16 = tile * 256 + (int)threadIdx.x;
+    const int row0 = seg * TC_WC_ROWS;
+    const int row1 = row0 + TC_WC_ROWS < rows_per_bl ? row0 + TC_WC_ROWS : rows_per_bl;
+    uint32_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0u;
+    if (f16 < F16) {
+        const uint4 *p = flags + (bl * rows_per_bl + row0) * (int64_t)F16 + f16;
+        int row = row0;
+        // four rows in flight per trip
+        for (; row + 4 <= row1; row += 4) {
+            uint4 w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) w[q] = p[(int64_t)q * F16];
+            p += 4 * (int64_t)F16;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                acc[0] += w[q].x & 0x00ff00ffu; acc[1] += (w[q].x >> 8) & 0x00ff00ffu;
+                acc[2] += w[q].y & 0x00ff00ffu; acc[3] += (w[q].y >> 8) & 0x00ff00ffu;
+                acc[4] += w[q].z & 0x00ff00ffu; acc[5] += (w[q].z >> 8) & 0x00ff00ffu;
+                acc[6] += w[q].w & 0x00ff00ffu; acc[7] += (w[q].w >> 8) & 0x00ff00ffu;
+            }
+        }
+        for (; row < row1; row++) {
+            const uint4 w = *p;
+            p += F16;
+            acc[0] += w.x & 0x00ff00ffu; acc[1] += (w.x >> 8) & 0x00ff00ffu;
+            acc[2] += w.y & 0x00ff00ffu; acc[3] += (w.y >> 8) & 0x00ff00ffu;
+            acc[4] += w.z & 0x00ff00ffu; acc[5] += (w.z >> 8) & 0x00ff00ffu;
+            acc[6] += w.w & 0x00ff00ffu; acc[7] += (w.w >> 8) & 0x00ff00ffu;
+        }
+    }
+    // column k of the thread: word k / 4, byte k % 4 -> acc[2 * (k / 4) + (k & 1)], field (k % 4) / 2
+    unsigned mine = 0;
+    if (f16 < F16) {
+        uint32_t *out = partial + (((int64_t)bl * gridDim.x + seg) * F16 + f16) * 16;
+        uint32_t col[16];
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++) {
+            col[4 * wd + 0] = acc[2 * wd] & 0xffffu;
+            col[4 * wd + 1] = acc[2 * wd + 1] & 0xffffu;
+            col[4 * wd + 2] = acc[2 * wd] >> 16;
+            col[4 * wd + 3] = acc[2 * wd + 1] >> 16;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) mine += col[k];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            reinterpret_cast<uint4 *>(out)[q] = make_uint4(col[4 * q], col[4 * q + 1], col[4 * q + 2], col[4 * q + 3]);
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(TC_FULL_MASK, mine, o);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 8; k++) t += s_tot[k];
+        if (t) atomicAdd(&bl_counts[bl], t);
+    }
+}
+
+// chan_counts[f] = sum over the (baseline, segment) slices; a thread owns one channel,
+// consecutive threads consecutive channels
+__global__ void __launch_bounds__(256)
+k_window_counts_fold(const uint32_t *__restrict__ partial, int64_t nslices, int F,
+                     unsigned long long *__restrict__ chan_counts)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    unsigned long long s = 0;
+    for (int64_t k = 0; k < nslices; k++) s += partial[k * F + f];
+    chan_counts[f] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_add_u64(unsigned long long *__restrict__ acc, const unsigned long long *__restrict__ x, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += x[i];
 }

@@ -429,6 +429,7 @@ int tc_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t 
         if (space == TC_HOST && !fill)
             TC_CUDA(cudaMemcpyAsync(dfw, flag_win, (size_t)nwin, cudaMemcpyHostToDevice, c->stream));
     }
+    tc_prof_begin(c, TCP_PACK);
     if (fill && nwin) {
         TC_LAUNCH_NOSYNC(k_fill_windows, tc_blocks_for(nwin, 256), 256, 0, c->stream, dvw, dfw, nwin);
         c->launches++;
@@ -446,6 +447,7 @@ int tc_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t 
         }
         c->launches++;
     }
+    tc_prof_end(c);
     TC_KERNEL_CHECK();
     if (vis && space == TC_HOST)
         TC_CUDA(cudaMemcpyAsync(vis_win, dvw, (size_t)nwin * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -472,28 +474,38 @@ int tc_unpack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_
     TC_TRY(tc_stage_in(c, (const char *)window, (size_t)nwin * elem_size, space, &dwin));
     TC_TRY(tc_stage_out_begin(c, (char *)out, (size_t)nout * elem_size, space, &dout));
     if (nout) {
-        if (elem_size == 8)
+        tc_prof_begin(c, TCP_PACK);
+        const bool al16 = ((((uintptr_t)dwin) | ((uintptr_t)dout)) & 15) == 0;
+        if (elem_size == 8 && ncorr == 4 && al16)
+            TC_LAUNCH_NOSYNC(k_unpack_vis_c4, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow,
+                             (const float2 *)dwin, (int)nchan, (int)ntime, (float4 *)dout);
+        else if (elem_size == 1 && ncorr == 4 && (nchan & 3) == 0 && al16)
+            TC_LAUNCH_NOSYNC(k_unpack_flags_c4<0>, tc_blocks_for(nrow * (nchan / 4), 256), 256, 0, c->stream, dbl, dt,
+                             nrow, (const uint32_t *)dwin, (int)(nchan / 4), (int)ntime, (uint4 *)dout);
+        else if (elem_size == 8)
             TC_LAUNCH_NOSYNC(k_unpack<float2>, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow,
                              (const float2 *)dwin, (int)nchan, (int)ncorr, (int)ntime, (float2 *)dout);
         else
             TC_LAUNCH_NOSYNC(k_unpack<u8>, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow,
                              (const u8 *)dwin, (int)nchan, (int)ncorr, (int)ntime, (u8 *)dout);
+        tc_prof_end(c);
         c->launches++;
         TC_KERNEL_CHECK();
     }
     return tc_stage_out_end(c, (char *)out, dout, (size_t)nout * elem_size, space);
 }
 
-int tc_unpack_flags_any_corr(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow,
-                             const uint8_t *window, int64_t nchan, int64_t ncorr, int64_t ntime, int64_t nbl,
-                             uint8_t *out, int space)
+int tc_unpack_flags_broadcast(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow,
+                              const uint8_t *window, int64_t nchan, int64_t ncorr_win, int64_t ncorr_out,
+                              int64_t ntime, int64_t nbl, uint8_t *out, int space)
 {
     TC_TRY(tc_begin(c));
+    TC_REQUIRE(ncorr_win >= 1 && ncorr_out >= 1, "correlation counts must be >= 1");
     for (int64_t r = 0; r < nrow; r++) {
         TC_REQUIRE(row_bl[r] < nbl, "row %lld: baseline slot %d out of range", (long long)r, row_bl[r]);
         TC_REQUIRE(row_bl[r] < 0 || (row_t[r] >= 0 && row_t[r] < ntime), "row %lld: time index out of range", (long long)r);
     }
-    int64_t nout = nrow * nchan * ncorr, nwin = nbl * ncorr * ntime * nchan;
+    int64_t nout = nrow * nchan * ncorr_out, nwin = nbl * ncorr_win * ntime * nchan;
     int32_t *dbl, *dt;
     TC_TRY(upload_i32(c, row_bl, (size_t)nrow, &dbl));
     TC_TRY(upload_i32(c, row_t, (size_t)nrow, &dt));
@@ -501,12 +513,77 @@ int tc_unpack_flags_any_corr(tc_context *c, const int32_t *row_bl, const int32_t
     TC_TRY(tc_stage_in(c, window, (size_t)nwin, space, &dwin));
     TC_TRY(tc_stage_out_begin(c, out, (size_t)nout, space, &dout));
     if (nout) {
-        TC_LAUNCH_NOSYNC(k_unpack_any_corr, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow, dwin,
-                         (int)nchan, (int)ncorr, (int)ntime, dout);
+        tc_prof_begin(c, TCP_PACK);
+        const bool al16 = ((((uintptr_t)dwin) | ((uintptr_t)dout)) & 15) == 0;
+        if (ncorr_win == 4 && ncorr_out == 4 && (nchan & 3) == 0 && al16)
+            TC_LAUNCH_NOSYNC(k_unpack_flags_c4<1>, tc_blocks_for(nrow * (nchan / 4), 256), 256, 0, c->stream, dbl, dt,
+                             nrow, (const uint32_t *)dwin, (int)(nchan / 4), (int)ntime, (uint4 *)dout);
+        else if (ncorr_win == 1 && ncorr_out == 4 && (nchan & 15) == 0 && al16)
+            TC_LAUNCH_NOSYNC(k_unpack_flags_c1_to4, tc_blocks_for(nrow * (nchan / 16), 256), 256, 0, c->stream, dbl, dt,
+                             nrow, (const uint4 *)dwin, (int)(nchan / 16), (int)ntime, (uint4 *)dout);
+        else
+            TC_LAUNCH_NOSYNC(k_unpack_any_corr, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow,
+                             dwin, (int)nchan, (int)ncorr_win, (int)ntime, (int)ncorr_out, dout);
+        tc_prof_end(c);
         c->launches++;
         TC_KERNEL_CHECK();
     }
     return tc_stage_out_end(c, out, dout, (size_t)nout, space);
+}
+
+int tc_unpack_flags_any_corr(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow,
+                             const uint8_t *window, int64_t nchan, int64_t ncorr, int64_t ntime, int64_t nbl,
+                             uint8_t *out, int space)
+{
+    return tc_unpack_flags_broadcast(c, row_bl, row_t, nrow, window, nchan, ncorr, ncorr, ntime, nbl, out, space);
+}
+
+// ---------------------------------------------------------- K2 + N2 + P1 ----
+int tc_stokes_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow, const void *vis,
+                   const uint8_t *flags, int64_t nchan, int64_t ncorr, int64_t ntime, int64_t nbl,
+                   const int32_t *unpol_idx, const double *unpol_coef, int nunpol, const int32_t *pol_idx,
+                   const double *pol_coef, int npol, void *vis_win, uint8_t *flag_win, int fill, int space)
+{
+    TC_TRY(tc_begin(c));
+    TC_REQUIRE(nrow >= 0 && nchan >= 0 && ntime >= 0 && nbl >= 0, "negative shape");
+    TC_REQUIRE(ncorr >= 1 && ncorr <= 8, "between 1 and 8 correlations are supported");
+    TC_REQUIRE(vis && flags && vis_win && flag_win, "null array");
+    StokesTerms pol, unpol;
+    memset(&unpol, 0, sizeof(unpol));
+    TC_TRY(fill_terms(&pol, pol_idx, pol_coef, npol, (int)ncorr));
+    if (nunpol > 0) TC_TRY(fill_terms(&unpol, unpol_idx, unpol_coef, nunpol, (int)ncorr));
+    for (int64_t r = 0; r < nrow; r++) {
+        TC_REQUIRE(row_bl[r] < nbl, "row %lld: baseline slot %d out of range", (long long)r, row_bl[r]);
+        TC_REQUIRE(row_bl[r] < 0 || (row_t[r] >= 0 && row_t[r] < ntime), "row %lld: time index %d out of range",
+                   (long long)r, row_t[r]);
+    }
+    int64_t nin = nrow * nchan * ncorr, nwin = nbl * ntime * nchan;
+    int32_t *dbl, *dt;
+    TC_TRY(upload_i32(c, row_bl, (size_t)nrow, &dbl));
+    TC_TRY(upload_i32(c, row_t, (size_t)nrow, &dt));
+    const float2 *dvis; const u8 *dfl; float2 *dvw; u8 *dfw;
+    TC_TRY(tc_stage_in(c, (const float2 *)vis, (size_t)nin, space, &dvis));
+    TC_TRY(tc_stage_in(c, flags, (size_t)nin, space, &dfl));
+    TC_TRY(tc_stage_out_begin(c, (float2 *)vis_win, (size_t)nwin, space, &dvw));
+    TC_TRY(tc_stage_out_begin(c, flag_win, (size_t)nwin, space, &dfw));
+    if (space == TC_HOST && !fill) {
+        TC_CUDA(cudaMemcpyAsync(dvw, vis_win, (size_t)nwin * 8, cudaMemcpyHostToDevice, c->stream));
+        TC_CUDA(cudaMemcpyAsync(dfw, flag_win, (size_t)nwin, cudaMemcpyHostToDevice, c->stream));
+    }
+    tc_prof_begin(c, TCP_PACK);
+    if (fill && nwin) {
+        TC_LAUNCH_NOSYNC(k_fill_windows, tc_blocks_for(nwin, 256), 256, 0, c->stream, dvw, dfw, nwin);
+        c->launches++;
+    }
+    if (nin) {
+        TC_LAUNCH_NOSYNC(k_stokes_pack, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow, dvis, dfl,
+                         (int)nchan, (int)ncorr, (int)ntime, pol, unpol, nunpol > 0 ? 1 : 0, dvw, dfw);
+        c->launches++;
+    }
+    tc_prof_end(c);
+    TC_KERNEL_CHECK();
+    TC_TRY(tc_stage_out_end(c, (float2 *)vis_win, dvw, (size_t)nwin, space));
+    return tc_stage_out_end(c, flag_win, dfw, (size_t)nwin, space);
 }
 
 // ------------------------------------------------------------------ W1 ------
@@ -524,15 +601,42 @@ int tc_window_counts(tc_context *c, const uint8_t *flags, int64_t nbl, int64_t n
     TC_CUDA(cudaMemsetAsync(dch, 0, sizeof(unsigned long long) * (size_t)(F > 0 ? F : 1), c->stream));
     if (total) {
         int64_t rows_per_bl = ncorr * T;
-        int rows_per_seg = 64;
-        // keep the per-thread column sum below 2^32 (flag bytes are <= 255)
-        unsigned segs = tc_blocks_for(rows_per_bl, rows_per_seg);
-        for (int64_t b0 = 0; b0 < nbl; b0 += 65535) {
-            int64_t nb = nbl - b0 < 65535 ? nbl - b0 : 65535;
-            TC_LAUNCH(k_window_counts, dim3(segs, (unsigned)nb), 256, 0, c->stream, dfl + b0 * rows_per_bl * F,
-                      rows_per_bl, rows_per_seg, (int)F, dbl + b0, dch);
-            c->launches++;
+        tc_prof_begin(c, TCP_STATS);
+        if ((F & 15) == 0 && (((uintptr_t)dfl) & 15) == 0 && rows_per_bl < ((int64_t)1 << 30)) {
+            // 16-byte row reads, per-block slices of column sums, one fold
+            const int F16 = (int)(F / 16);
+            const unsigned segs = tc_blocks_for(rows_per_bl, TC_WC_ROWS), tiles = tc_blocks_for(F16, 256);
+            TC_REQUIRE(tiles <= 65535, "too many channels");
+            for (int64_t b0 = 0; b0 < nbl; b0 += 4096) {
+                const int64_t nb = nbl - b0 < 4096 ? nbl - b0 : 4096;
+                tc_mark mark = tc_arena_mark(c);
+                uint32_t *partial;
+                unsigned long long *dchp = dch;
+                TC_TRY(tc_alloc(c, (size_t)nb * segs * F, &partial));
+                if (b0 > 0) TC_TRY(tc_alloc(c, (size_t)F, &dchp));
+                TC_LAUNCH(k_window_counts_v16, dim3(segs, tiles, (unsigned)nb), 256, 0, c->stream,
+                          (const uint4 *)(dfl + b0 * rows_per_bl * F), (int)rows_per_bl, F16, partial, dbl + b0);
+                TC_LAUNCH_NOSYNC(k_window_counts_fold, tc_blocks_for(F, 256), 256, 0, c->stream, partial, nb * segs, (int)F,
+                                 dchp);
+                c->launches += 2;
+                if (b0 > 0) {
+                    TC_LAUNCH_NOSYNC(k_add_u64, tc_blocks_for(F, 256), 256, 0, c->stream, dch, dchp, F);
+                    c->launches++;
+                }
+                tc_arena_release(c, mark);
+            }
+        } else {
+            int rows_per_seg = 64;
+            // keep the per-thread column sum below 2^32 (flag bytes are <= 255)
+            unsigned segs = tc_blocks_for(rows_per_bl, rows_per_seg);
+            for (int64_t b0 = 0; b0 < nbl; b0 += 65535) {
+                int64_t nb = nbl - b0 < 65535 ? nbl - b0 : 65535;
+                TC_LAUNCH(k_window_counts, dim3(segs, (unsigned)nb), 256, 0, c->stream, dfl + b0 * rows_per_bl * F,
+                          rows_per_bl, rows_per_seg, (int)F, dbl + b0, dch);
+                c->launches++;
+            }
         }
+        tc_prof_end(c);
         TC_KERNEL_CHECK();
     }
     if (nbl) TC_CUDA(cudaMemcpyAsync(bl_counts, dbl, sizeof(uint64_t) * (size_t)nbl, cudaMemcpyDeviceToHost, c->stream));

@@ -177,13 +177,16 @@ def unpack_data(antenna1, antenna2, time_inv, ubl, flag_windows):
     return out if out.dtype == wa.dtype else out.astype(wa.dtype)
 
 
-def unpack_flags_equalised(antenna1, antenna2, time_inv, ubl, flag_windows):
+def unpack_flags_equalised(antenna1, antenna2, time_inv, ubl, flag_windows, ncorr_out=None):
     """``unpack_data`` fused with the app's correlation equalisation
     (tricolour/apps/tricolour/app.py:479-480): a sample flagged in any
-    correlation is flagged in all of them."""
+    correlation is flagged in all ``ncorr_out`` correlations of the output rows
+    (default: the window's own count; a one-correlation window of the polarised
+    strategies is broadcast to the measurement set's correlations this way)."""
     ubl = np.asarray(ubl)
     w = flag_windows
     nbl, ncorr, ntime, nchan = (int(s) for s in w.shape)
+    nout = ncorr if ncorr_out is None else int(ncorr_out)
     u = ubl.copy()
     if u.shape[0]:
         u[:, 0] = u[:, 0] - u[:, 0].min()
@@ -192,19 +195,82 @@ def unpack_flags_equalised(antenna1, antenna2, time_inv, ubl, flag_windows):
     if _cabi.is_device_array(w):
         import torch
         raw = w.contiguous().view(torch.uint8)
-        out = torch.empty((nrow, nchan, ncorr), dtype=torch.uint8, device=w.device)
+        out = torch.empty((nrow, nchan, nout), dtype=torch.uint8, device=w.device)
     else:
         wa = np.asarray(w)
         raw = (np.ascontiguousarray(wa).view(np.uint8) if wa.dtype.itemsize == 1
                else np.ascontiguousarray(wa != 0).view(np.uint8))
-        out = np.empty((nrow, nchan, ncorr), np.uint8)
+        out = np.empty((nrow, nchan, nout), np.uint8)
     ctx, space = context_for(raw)
-    check(_cabi.load().tc_unpack_flags_any_corr(ctx.handle, _hp(slot), _hp(t), nrow, ptr(raw), nchan,
-                                                ncorr, ntime, nbl, ptr(out), space))
+    check(_cabi.load().tc_unpack_flags_broadcast(ctx.handle, _hp(slot), _hp(t), nrow, ptr(raw), nchan,
+                                                 ncorr, nout, ntime, nbl, ptr(out), space))
     if _cabi.is_device_array(w):
         import torch
         return out.view(torch.bool)
     return out.view(np.bool_)
+
+
+def pack_polarised(time_inv, ubl, antenna1, antenna2, data, flags, ntime, stokes_pol, stokes_unpol=None):
+    """The polarised / total-power front end of the application in one pass over
+    the rows (app.py:415-432 followed by ``pack_data``): Stokes intensity of the
+    correlations (``polarised_intensity``, or ``unpolarised_intensity`` when
+    ``stokes_unpol`` is given), ``flags.any(axis=2)`` and the scatter into windows
+    of shape (bl, 1, time, chan).  Equal to
+    ``pack_data(..., polarised_intensity(data, stokes_pol), flags.any(2, keepdims=True), ntime)``."""
+    from .stokes import _terms
+    nrow, nchan, ncorr = (int(s) for s in data.shape)
+    if tuple(flags.shape) != tuple(data.shape):
+        raise ValueError("vis_windows.shape != flag_windows.shape")
+    if stokes_unpol is not None and not len(stokes_unpol) == 1:
+        raise ValueError("There should be exactly one entry "
+                         "for unpolarised stokes (stokes_unpol)")
+    if not len(stokes_pol) > 0:
+        raise ValueError("No entries for polarised stokes (stokes_pol)")
+    ubl = np.asarray(ubl)
+    nbl = int(ubl.shape[0])
+    slot, t = _row_slots(ubl, antenna1, antenna2, time_inv, last_wins=True)
+    if slot.size and t[slot >= 0].size and (t[slot >= 0].min() < 0 or t[slot >= 0].max() >= ntime):
+        raise ValueError("time_inv out of range")
+    dev = _cabi.is_device_array(data)
+    if dev != _cabi.is_device_array(flags):
+        raise TypeError("tricolour_b200: data and flags must both be numpy arrays or both be CUDA tensors")
+    if dev:
+        import torch
+        vis = data.contiguous()
+        if vis.dtype != torch.complex64:
+            raise TypeError("device visibilities must be complex64")
+        fl = flags.contiguous()
+        fdt = fl.dtype
+        fl8 = fl.view(torch.uint8) if fdt in (torch.bool, torch.uint8) else (fl != 0).view(torch.uint8)
+        vis_win = torch.empty((nbl, 1, int(ntime), nchan), dtype=torch.complex64, device=vis.device)
+        flag_win = torch.empty((nbl, 1, int(ntime), nchan), dtype=torch.uint8, device=vis.device)
+    else:
+        vis_in = np.asarray(data)
+        vdt = vis_in.dtype
+        vis = np.ascontiguousarray(vis_in, dtype=np.complex64)
+        f = np.asarray(flags)
+        fdt = f.dtype
+        fl8 = (np.ascontiguousarray(f).view(np.uint8) if f.dtype.itemsize == 1
+               else np.ascontiguousarray(f != 0).view(np.uint8))
+        vis_win = np.empty((nbl, 1, int(ntime), nchan), np.complex64)
+        flag_win = np.empty((nbl, 1, int(ntime), nchan), np.uint8)
+    pi, pc = _terms(stokes_pol)
+    if stokes_unpol is not None:
+        ui, uc = _terms(stokes_unpol)
+    else:
+        ui, uc = np.zeros((0, 2), np.int32), np.zeros((0, 4), np.float64)
+    ctx, space = context_for(vis, fl8)
+    check(_cabi.load().tc_stokes_pack(ctx.handle, _hp(slot), _hp(t), nrow, ptr(vis), ptr(fl8), nchan, ncorr,
+                                      int(ntime), nbl, _hp(ui), _hp(uc), ui.shape[0], _hp(pi), _hp(pc),
+                                      pi.shape[0], ptr(vis_win), ptr(flag_win), 1, space))
+    if dev:
+        import torch
+        flag_win = flag_win.view(torch.bool) if fdt == torch.bool else flag_win.to(fdt)
+    else:
+        if vdt != np.complex64:
+            vis_win = vis_win.astype(vdt)
+        flag_win = flag_win.view(np.bool_) if fdt == np.bool_ else flag_win.astype(fdt)
+    return vis_win, flag_win
 
 
 # ---------------------------------------------------------------------------

@@ -184,6 +184,57 @@ def test_time_median(backend):
         assert_same(b, b2)
 
 
+def test_line_median_adversarial(backend):
+    """the interpolation-search line median on inputs that stress its bracket logic:
+    massive ties at the median (more equal keys than the 32-key finishing stage holds),
+    two-valued and constant lines, 60 decades of dynamic range, signed data, even / odd
+    counts, nearly fully flagged lines, every register tiling (T = 1 ... 1024)"""
+    rs = np.random.RandomState(44)
+    Ts = ((1, 2, 3, 31, 32, 33, 64, 100, 129, 257, 512, 600, 1000, 1024, 1025, 3277) if big(backend)
+          else (1, 2, 3, 33, 64, 100, 257, 600, 1100))
+    for T in Ts:
+        F = 16
+        d = rs.standard_normal((T, F)).astype(np.float32)
+        d[:, 1] = np.round(d[:, 1] * 2) / 2                     # heavy ties around the median
+        d[:, 2] = 1.0                                           # constant
+        d[:, 3] = rs.randint(0, 2, T)                           # two values
+        d[:, 4] = (d[:, 4] * 10.0 ** rs.uniform(-30, 30, T)).astype(np.float32)
+        d[:, 5] = np.abs(d[:, 5]) + 2.3                         # one binade
+        d[:, 6] = np.where(rs.uniform(size=T) < 0.5, 0.75, d[:, 6])   # half the line equal
+        d[:, 7] = np.sort(d[:, 7])
+        d[:, 8] = -np.abs(d[:, 8])                              # negative only
+        d[:, 9] = np.float32(1e-42) * rs.randint(0, 5, T)       # float32 denormals and zeros
+        for pf in (0.0, 0.3, 0.9):
+            fl = rs.uniform(size=d.shape) < pf
+            fl[:, 10] = True
+            fl[: T // 2, 11] = True
+            if T > 1:
+                fl[0, 12] = not fl[1:, 12].sum() % 2               # force an odd / even count
+            a, b = G._time_median(d, fl)
+            a2, b2 = oracle._time_median(d, fl)
+            assert_same(a, a2, "time median T=%d pf=%.1f" % (T, pf))
+            assert_same(b, b2)
+    # chunked |x| medians behind the SumThreshold thresholds (LM_ST_THRESHOLD), both axes
+    T, F = (96, 410) if big(backend) else (24, 70)
+    d = (rs.standard_normal((2, T, F)) * 10 ** rs.uniform(-3, 1, (2, T, F))).astype(np.float32)
+    d[0, :, 5] = 0.5
+    fl = rs.uniform(size=d.shape) < 0.4
+    ce = np.linspace(0, F, 4).astype(int)
+    for axis, ch in ((0, None), (1, ce)):
+        got = G._sum_threshold(d, fl, axis, np.array([1, 2, 4, 8]), 10, 1.3, ch)
+        for p in range(2):
+            want = oracle._sum_threshold(d[p], fl[p], axis, np.array([1, 2, 4, 8]), 10, 1.3, ch)
+            assert_same(got[p], want, "thresholds axis %d" % axis)
+    # frequency chunks longer than 1024 channels (the 32768-channel mode): re-reading form
+    T, F = (16, 6600) if big(backend) else (3, 2300)
+    d = (rs.standard_normal((1, T, F)) * 10 ** rs.uniform(-3, 1, (1, T, F))).astype(np.float32)
+    fl = rs.uniform(size=d.shape) < 0.4
+    ce = np.array([0, 1100, F])
+    got = G._sum_threshold(d, fl, 1, np.array([1, 2, 4, 8]), 10, 1.3, ce)
+    want = oracle._sum_threshold(d[0], fl[0], 1, np.array([1, 2, 4, 8]), 10, 1.3, ce)
+    assert_same(got[0], want, "long chunk thresholds")
+
+
 def test_median_abs(backend):
     data = np.array([[-2.0, -6.0, 4.5], [1.5, 3.3, 0.5]], np.float32)
     flags = np.array([[0, 0, 0], [0, 1, 0]], np.uint8)

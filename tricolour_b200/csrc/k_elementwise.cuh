@@ -46,6 +46,7 @@ static int launch_flag_nans_zeros(tc_context *c, const void *vis, const u8 *flag
 {
     bool aligned = (((uintptr_t)vis & 15) == 0) && (((uintptr_t)flags & 3) == 0) && (((uintptr_t)out & 3) == 0);
     int64_t n4 = aligned ? n / 4 : 0;
+    tc_prof_begin(c, TCP_ELEMENTWISE);
     if (n4 > 0) {
         TC_LAUNCH_NOSYNC(k_flag_nans_zeros_v4, tc_blocks_for(n4, 256), 256, 0, c->stream,
                          (const float4 *)vis, (const uint32_t *)flags, (uint32_t *)out, n4);
@@ -57,6 +58,7 @@ static int launch_flag_nans_zeros(tc_context *c, const void *vis, const u8 *flag
                          (const float2 *)vis, flags, out, n, n4 * 4);
         c->launches++;
     }
+    tc_prof_end(c);
     TC_KERNEL_CHECK();
     return TC_OK;
 }
@@ -123,6 +125,7 @@ static int launch_apply_mask(tc_context *c, const u8 *flags, const u8 *bl_sel_de
     if (total == 0) return TC_OK;
     bool vec = (nchan % 16 == 0) && (((uintptr_t)flags & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
                (((uintptr_t)chan_mask_dev & 15) == 0);
+    tc_prof_begin(c, TCP_ELEMENTWISE);
     if (vec) {
         int64_t t16 = total / 16;
         TC_LAUNCH_NOSYNC(k_apply_mask_v16, tc_blocks_for(t16, 256), 256, 0, c->stream,
@@ -132,6 +135,7 @@ static int launch_apply_mask(tc_context *c, const u8 *flags, const u8 *bl_sel_de
         TC_LAUNCH_NOSYNC(k_apply_mask, tc_blocks_for(total, 256), 256, 0, c->stream, flags,
                          bl_sel_dev, chan_mask_dev, mode, rows_per_bl, nchan, total, out);
     }
+    tc_prof_end(c);
     c->launches++;
     TC_KERNEL_CHECK();
     return TC_OK;
@@ -160,6 +164,7 @@ static int launch_or(tc_context *c, const u8 *a, const u8 *b, u8 *out, int64_t n
 {
     bool aligned = ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0;
     int64_t n16 = aligned ? n / 16 : 0;
+    tc_prof_begin(c, TCP_ELEMENTWISE);
     if (n16 > 0) {
         TC_LAUNCH_NOSYNC(k_or_v16, tc_blocks_for(n16, 256), 256, 0, c->stream, (const uint4 *)a,
                          (const uint4 *)b, (uint4 *)out, n16);
@@ -169,6 +174,7 @@ static int launch_or(tc_context *c, const u8 *a, const u8 *b, u8 *out, int64_t n
         TC_LAUNCH_NOSYNC(k_or, tc_blocks_for(n - n16 * 16, 256), 256, 0, c->stream, a, b, out, n, n16 * 16);
         c->launches++;
     }
+    tc_prof_end(c);
     TC_KERNEL_CHECK();
     return TC_OK;
 }

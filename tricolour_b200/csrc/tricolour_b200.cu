@@ -366,8 +366,10 @@ static int stokes_common(tc_context *c, const void *vis, int64_t n, int ncorr, c
     TC_TRY(tc_stage_in(c, (const float2 *)vis, (size_t)n * ncorr, space, &dvis));
     TC_TRY(tc_stage_out_begin(c, (float2 *)out, (size_t)n, space, &dout));
     if (n) {
+        tc_prof_begin(c, TCP_ELEMENTWISE);
         TC_LAUNCH_NOSYNC(k_stokes, tc_blocks_for(n, 256), 256, 0, c->stream, dvis, n, ncorr, pol, unpol,
                          with_unpol, dout);
+        tc_prof_end(c);
         c->launches++;
         TC_KERNEL_CHECK();
     }

@@ -156,20 +156,13 @@ def flag_autos(flags, ubl):
 # ---------------------------------------------------------------------------
 # F3 apply_static_mask (tricolour/flagging.py:98-172)
 # ---------------------------------------------------------------------------
-def apply_static_mask(flag, ubl, antspos, masks,
-                      chan_freqs, chan_widths,
-                      accumulation_mode="or", uvrange=""):
-    """Applies static masks, flagging channels that span frequencies included
-    in a mask, for the baselines whose length lies inside ``uvrange``.
-
-    Same arguments as the reference; ``masks`` is a list of (n, 1) float64
-    arrays of masked frequencies in Hz.
-    """
+def _static_mask_tables(ubl, antspos, masks, chan_freqs, chan_widths, accumulation_mode, uvrange):
+    """(baseline selector u8[nbl], channel mask u8[nchan], kernel mode): the host-side
+    part of apply_static_mask (flagging.py:125-166), O(nbl) + O(mask frequencies x nchan)
+    float64 work on metadata.  The StrategyExecutor keeps the result per task, since
+    the same tables serve every block of an observation."""
     uvrange = casa_style_range(uvrange)
     ubl = np.asarray(ubl)
-    if flag.shape[0] != ubl.shape[0]:
-        raise ValueError("flag and ubl shape mismatch %s != %s"
-                         % (flag.shape[1], ubl.shape[0]))
     chan_freqs = np.asarray(chan_freqs)
     chan_widths = np.asarray(chan_widths)
     spw_chanlb = chan_freqs - chan_widths * 0.5
@@ -198,24 +191,45 @@ def apply_static_mask(flag, ubl, antspos, masks,
         else:
             raise ValueError("Invalid accumulation_mode '%s'. "
                              "Should be 'or' or 'override'" % accumulation_mode)
+    if combined is None:
+        # no masks: plain copy
+        combined = np.zeros(chan_freqs.shape[0], np.bool_)
+        mode = 0
+    else:
+        mode = 0 if accumulation_mode == "or" else 1
+    sel = np.ascontiguousarray(bl_sel).view(np.uint8)
+    cm = np.ascontiguousarray(combined).view(np.uint8)
+    return sel, cm, mode
 
+
+def _apply_mask_tables(flag, tables):
+    sel, cm, mode = tables
     fl, restore = _as_u8_flags(flag)
     ctx, space = context_for(fl)
     out = _empty_u8_like(fl)
     nbl = int(fl.shape[0])
     nchan = int(fl.shape[-1])
     rows = int(np.prod(fl.shape[1:-1])) if nbl else 0
-    if combined is None:
-        # no masks: plain copy
-        combined = np.zeros(nchan, np.bool_)
-        mode = 0
-    else:
-        mode = 0 if accumulation_mode == "or" else 1
-    sel = np.ascontiguousarray(bl_sel).view(np.uint8)
-    cm = np.ascontiguousarray(combined).view(np.uint8)
     check(_cabi.load().tc_apply_channel_mask(ctx.handle, ptr(fl), _hp(sel), _hp(cm), mode,
                                              nbl, rows, nchan, ptr(out), space))
     return restore(out)
+
+
+def apply_static_mask(flag, ubl, antspos, masks,
+                      chan_freqs, chan_widths,
+                      accumulation_mode="or", uvrange=""):
+    """Applies static masks, flagging channels that span frequencies included
+    in a mask, for the baselines whose length lies inside ``uvrange``.
+
+    Same arguments as the reference; ``masks`` is a list of (n, 1) float64
+    arrays of masked frequencies in Hz.
+    """
+    ubl = np.asarray(ubl)
+    if flag.shape[0] != ubl.shape[0]:
+        raise ValueError("flag and ubl shape mismatch %s != %s"
+                         % (flag.shape[1], ubl.shape[0]))
+    tables = _static_mask_tables(ubl, antspos, masks, chan_freqs, chan_widths, accumulation_mode, uvrange)
+    return _apply_mask_tables(flag, tables)
 
 
 # ---------------------------------------------------------------------------

@@ -18,7 +18,7 @@ import numpy as np
 from . import _cabi
 from ._cabi import check, ptr
 from .flagging import (sum_threshold_flagger, uvcontsub_flagger, flag_autos,
-                       flag_nans_and_zeros, apply_static_mask)
+                       flag_nans_and_zeros, _static_mask_tables, _apply_mask_tables)
 
 
 def load_strategies(path):
@@ -265,9 +265,16 @@ class StrategyExecutor(object):
             elif task == "flag_nans_zeros":
                 flag_windows = flag_nans_and_zeros(vis_windows, flag_windows)
             elif task == "apply_static_mask":
-                new_flags = apply_static_mask(flag_windows, ubl, self.ant_pos,
-                                              self.masked_channels, self.chan_freq,
-                                              self.chan_width, **kwargs)
+                if flag_windows.shape[0] != ubl.shape[0]:
+                    raise ValueError("flag and ubl shape mismatch %s != %s"
+                                     % (flag_windows.shape[1], ubl.shape[0]))
+                # the selector tables depend on observation metadata only: built once per task
+                cache = self.__dict__.setdefault("_mask_tables", {})
+                key = (kwargs.get("accumulation_mode", "or"), kwargs.get("uvrange", ""))
+                if key not in cache:
+                    cache[key] = _static_mask_tables(ubl, self.ant_pos, self.masked_channels, self.chan_freq,
+                                                     self.chan_width, *key)
+                new_flags = _apply_mask_tables(flag_windows, cache[key])
                 if kwargs["accumulation_mode"].strip() == "or":
                     flag_windows = _flags_or(new_flags, flag_windows)
                 else:

@@ -359,6 +359,38 @@ def test_masked_gaussian_filter_radii(backend):
         assert_same(o, o2, "masked filter (thread per line) radii (%d, %d) shape %s" % (r0, r1, shape))
 
 
+def test_masked_gaussian_filter_thread_per_line(backend):
+    """the skewed thread-per-line kernels (k_filter3.cuh): every ring phase (radius mod 2,
+    one-vector rings), lines that do not fill the last warp, several planes, the largest
+    radii each form takes (54 on the first axis, 34 on the second), tiles of the second
+    axis that end inside a 16-sample block, 60 decades of dynamic range in one plane
+    (the drain's safe-range test must send those groups to the plain divisions)"""
+    rs = np.random.RandomState(67)
+    if big(backend):
+        cases = [((3, 64, 100), (2, 2)), ((2, 48, 132), (3, 3)), ((1, 512, 96), (54, 34)), ((2, 128, 260), (21, 25)),
+                 ((1, 32, 4096), (10, 8)), ((2, 80, 72), (43, 17)), ((1, 16, 40), (5, 12)), ((1, 256, 68), (32, 9))]
+    else:
+        cases = [((2, 16, 40), (2, 2)), ((1, 32, 36), (3, 3)), ((1, 16, 20), (9, 7)), ((2, 48, 24), (14, 5))]
+    for shape, (r0, r1) in cases:
+        sig = np.array((_sigma_for_radius(r0), _sigma_for_radius(r1)))
+        d = (rs.uniform(size=shape) * 10 ** rs.uniform(-2, 2, shape)).astype(np.float32)
+        d[0, : shape[1] // 3] *= (10.0 ** rs.uniform(-30, 28, (shape[1] // 3, shape[2]))).astype(np.float32)
+        fl = rs.uniform(size=shape) < 0.35
+        fl[:, shape[1] // 2:, : shape[2] // 3] = True
+        o = np.zeros_like(d)
+        G.masked_gaussian_filter(d, fl, sig, o)
+        for p in range(shape[0]):
+            o2 = np.zeros_like(d[p])
+            oracle.masked_gaussian_filter(d[p], fl[p], sig, o2)
+            assert_same(o[p], o2, "thread-per-line filter %s r=(%d, %d) plane %d" % (shape, r0, r1, p))
+        # residual form through the background loop
+        ce = np.linspace(0, shape[2], 4).astype(int)
+        bg = G._get_background2d(d, fl, 2, np.array((r0 * 0.6 + 1, r1 * 0.6 + 1)), 2.0, ce)
+        for p in range(shape[0]):
+            want = oracle._get_background2d(d[p], fl[p], 2, np.array((r0 * 0.6 + 1, r1 * 0.6 + 1)), 2.0, ce)
+            assert_same(bg[p], want, "background %s plane %d" % (shape, p))
+
+
 def test_masked_gaussian_filter_dynamic_range(backend):
     """samples spanning 60 decades (incl. float32 denormals and exact zeros): the
     exact-division shortcut and the integer-pipe widening must still agree bit for bit"""

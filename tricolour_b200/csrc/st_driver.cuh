@@ -13,6 +13,7 @@
 #include "k_elementwise.cuh"
 #include "k_filter.cuh"
 #include "k_filter2.cuh"
+#include "k_filter3.cuh"
 #include "k_select.cuh"
 #include "k_sumthreshold.cuh"
 
@@ -89,14 +90,22 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     probe.n = Fa; probe.r = (int)r1;
     const bool lean1 = r1 > 0 && b2_supported(c, probe) && (r0 > 0 || T == 1);
     if (r0 > 0 && r1 > 0) {
+        // second axis first: which kernel takes it decides the layout of the intermediate pair
+        FilterArgs b;
+        memset(&b, 0, sizeof(b));
+        b.n = Fa; b.nj = T; b.nlines = np * T; b.r = (int)r1;
+        b.mode_in = FIN_PAIR; b.mode_out = resid ? FOUT_RESID : FOUT_BG;
+        b.data = w.v_FT; b.win = w.w_FT; b.vout = out_FT;
+        const bool tplb = tpl_b_supported(c, b);
         // time axis: flags are read from the (F,T) layout; the pair goes to (T,F)
-        // when the lean frequency kernel follows, else to (F,T)
+        // when a kernel that reads line-contiguous input follows, else to (F,T)
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
-        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = lean1 ? 0 : 1;
+        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = (lean1 || tplb) ? 0 : 1;
         a.vout = w.v_FT; a.wout = w.w_FT;
         a.data = data_TF;
-        if (t4a_supported(c, a)) TC_TRY(launch_box_t4a(c, a));
+        if (tpl_a_supported(c, a)) TC_TRY(launch_box_tpl_a(c, a));
+        else if (t4a_supported(c, a)) TC_TRY(launch_box_t4a(c, a));
         else if (lean0 && t4a_weights_supported(c, a)) {
             // values: lane-per-chain kernel; weights: thread-per-line integer chains
             a.role = 2;
@@ -105,16 +114,16 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
             TC_TRY(launch_box_filter2(c, a));
         } else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
         else TC_TRY(launch_box_filter(c, a));
-        memset(&a, 0, sizeof(a));
-        a.n = Fa; a.nj = T; a.nlines = np * T; a.r = (int)r1;
-        a.mode_in = FIN_PAIR; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
-        a.data = w.v_FT; a.win = w.w_FT; a.vout = out_FT;
-        if (lean1) {
+        if (tplb) {
+            // thread per line: the output is sample-major for this axis, i.e. (F,T)
+            b.data2 = data_FT;
+            TC_TRY(launch_box_tpl_b(c, b));
+        } else if (lean1) {
             // the lean kernel can leave its output line-contiguous, i.e. in (T,F)
-            a.data2 = data_TF;
-            if (want_TF && got_TF) { a.out_transposed = 1; *got_TF = 1; }
-            TC_TRY(launch_box_filter2(c, a));
-        } else { a.data2 = data_FT; TC_TRY(launch_box_filter(c, a)); }
+            b.data2 = data_TF;
+            if (want_TF && got_TF) { b.out_transposed = 1; *got_TF = 1; }
+            TC_TRY(launch_box_filter2(c, b));
+        } else { b.data2 = data_FT; TC_TRY(launch_box_filter(c, b)); }
     } else if (r0 > 0) {
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0; a.single_axis = 1;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;

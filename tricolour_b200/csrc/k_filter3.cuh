@@ -320,7 +320,9 @@ static int tpl_env_int(const char *name, int dflt)
 static bool tpl_a_supported(tc_context *c, const FilterArgs &a)
 {
     static const int max_r = tpl_env_int("TC_TPL_A_MAXR", 54);
-    if (TC_ENV_FLAG("TC_FILTER_NO_TPL") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
+    // measured slower than the k_filter2.cuh forms at every radius of default.yaml
+    // (profiles/r02_filter_ab.txt): an experiment knob, off by default
+    if (!TC_ENV_FLAG("TC_TPL_A") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
     if (a.r < 2 || a.r > max_r || (a.n & 15)) return false;
     if (a.mode_in != FIN_MASKED || a.mode_out != FOUT_PAIR || !a.flags_transposed) return false;
     return (tpl_a_per_warp(a.r) + 1024) * TPL_MIN_WARPS_SM <= (size_t)c->smem_optin + 1024;
@@ -330,7 +332,7 @@ static bool tpl_b_supported(tc_context *c, const FilterArgs &a)
 {
     static const int max_r = tpl_env_int("TC_TPL_B_MAXR", 34);
     static const int min_warps = tpl_env_int("TC_TPL_B_MINW", 3);
-    if (TC_ENV_FLAG("TC_FILTER_NO_TPL") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
+    if (!TC_ENV_FLAG("TC_TPL_B") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
     if (a.r < 2 || a.r > max_r || (a.n & 3)) return false;
     if (a.mode_in != FIN_PAIR || (a.mode_out != FOUT_BG && a.mode_out != FOUT_RESID)) return false;
     if ((((uintptr_t)a.data | (uintptr_t)a.win) & 15) != 0) return false;

@@ -14,6 +14,7 @@
 #include "k_filter.cuh"
 #include "k_filter2.cuh"
 #include "k_filter3.cuh"
+#include "k_filter5.cuh"
 #include "k_select.cuh"
 #include "k_sumthreshold.cuh"
 
@@ -89,6 +90,17 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     const bool lean0 = r0 > 0 && b2_supported(c, probe);
     probe.n = Fa; probe.r = (int)r1;
     const bool lean1 = r1 > 0 && b2_supported(c, probe) && (r0 > 0 || T == 1);
+    // the B5 forms (k_filter5.cuh) replace the lane-per-chain kernels of k_filter2.cuh
+    // wherever they apply; TC_B5_A_MINR / TC_B5_B_MINR keep an axis on the older forms
+    // below a radius (the thread-per-line kernel of small first-axis radii)
+    // (measured on B200, profiles/r02_filter_probe.txt: first axis from r = 37, where the thread-per-line
+    // weight chains stop; second axis up to r ~ 200, beyond which the longer rings cost occupancy)
+    static const int b5_a_minr = tpl_env_int("TC_B5_A_MINR", 37), b5_b_minr = tpl_env_int("TC_B5_B_MINR", 1);
+    static const int b5_b_maxr = tpl_env_int("TC_B5_B_MAXR", 200);
+    probe.n = T; probe.r = (int)r0; probe.data = data_FT; probe.flags = w.fl_FT;
+    const bool b5_0 = r0 >= b5_a_minr && r0 > 0 && b5_supported(c, probe);
+    probe.n = Fa; probe.r = (int)r1; probe.data = w.v_FT; probe.win = w.w_FT; probe.flags = nullptr;
+    const bool b5_1 = r1 >= b5_b_minr && r1 <= b5_b_maxr && r1 > 0 && b5_supported(c, probe) && (r0 > 0 || T == 1);
     if (r0 > 0 && r1 > 0) {
         // second axis first: which kernel takes it decides the layout of the intermediate pair
         FilterArgs b;
@@ -96,15 +108,16 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         b.n = Fa; b.nj = T; b.nlines = np * T; b.r = (int)r1;
         b.mode_in = FIN_PAIR; b.mode_out = resid ? FOUT_RESID : FOUT_BG;
         b.data = w.v_FT; b.win = w.w_FT; b.vout = out_FT;
-        const bool tplb = tpl_b_supported(c, b);
+        const bool tplb = !b5_1 && tpl_b_supported(c, b);
         // time axis: flags are read from the (F,T) layout; the pair goes to (T,F)
         // when a kernel that reads line-contiguous input follows, else to (F,T)
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_PAIR;
-        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = (lean1 || tplb) ? 0 : 1;
+        a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = (b5_1 || lean1 || tplb) ? 0 : 1;
         a.vout = w.v_FT; a.wout = w.w_FT;
         a.data = data_TF;
-        if (tpl_a_supported(c, a)) TC_TRY(launch_box_tpl_a(c, a));
+        if (b5_0) { a.data = data_FT; TC_TRY(launch_box_filter5(c, a)); }
+        else if (tpl_a_supported(c, a)) TC_TRY(launch_box_tpl_a(c, a));
         else if (t4a_supported(c, a)) TC_TRY(launch_box_t4a(c, a));
         else if (lean0 && t4a_weights_supported(c, a)) {
             // values: lane-per-chain kernel; weights: thread-per-line integer chains
@@ -114,22 +127,24 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
             TC_TRY(launch_box_filter2(c, a));
         } else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
         else TC_TRY(launch_box_filter(c, a));
-        if (tplb) {
+        if (b5_1 || (!tplb && lean1)) {
+            // the lane-per-chain kernels can leave their output line-contiguous, i.e. in (T,F)
+            b.data2 = data_TF;
+            if (want_TF && got_TF) { b.out_transposed = 1; *got_TF = 1; }
+            if (b5_1) TC_TRY(launch_box_filter5(c, b));
+            else TC_TRY(launch_box_filter2(c, b));
+        } else if (tplb) {
             // thread per line: the output is sample-major for this axis, i.e. (F,T)
             b.data2 = data_FT;
             TC_TRY(launch_box_tpl_b(c, b));
-        } else if (lean1) {
-            // the lean kernel can leave its output line-contiguous, i.e. in (T,F)
-            b.data2 = data_TF;
-            if (want_TF && got_TF) { b.out_transposed = 1; *got_TF = 1; }
-            TC_TRY(launch_box_filter2(c, b));
         } else { b.data2 = data_FT; TC_TRY(launch_box_filter(c, b)); }
     } else if (r0 > 0) {
         a.n = T; a.nj = Fa; a.nlines = np * Fa; a.r = (int)r0; a.single_axis = 1;
         a.mode_in = FIN_MASKED; a.mode_out = FOUT_BG;
         a.flags = w.fl_FT; a.flags_transposed = 1; a.out_transposed = 1;
         a.vout = out_FT;
-        if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
+        if (b5_0) { a.data = data_FT; TC_TRY(launch_box_filter5(c, a)); }
+        else if (lean0) { a.data = data_FT; TC_TRY(launch_box_filter2(c, a)); }
         else { a.data = data_TF; TC_TRY(launch_box_filter(c, a)); }
         if (resid) {
             TC_LAUNCH_NOSYNC(k_abs_sub, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, out_FT, out_FT, N);
@@ -140,7 +155,8 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
         a.mode_in = FIN_MASKED; a.mode_out = resid ? FOUT_RESID : FOUT_BG;
         a.data = data_FT; a.flags = w.fl_FT; a.vout = out_FT; a.data2 = data_FT;
         // T == 1: both layouts coincide and the lines are contiguous
-        if (lean1) TC_TRY(launch_box_filter2(c, a));
+        if (b5_1) TC_TRY(launch_box_filter5(c, a));
+        else if (lean1) TC_TRY(launch_box_filter2(c, a));
         else TC_TRY(launch_box_filter(c, a));
     } else {
         TC_LAUNCH_NOSYNC(k_masked_copy, tc_blocks_for(N, 256), 256, 0, c->stream, data_FT, w.fl_FT, N,

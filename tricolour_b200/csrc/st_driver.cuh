@@ -15,6 +15,7 @@
 #include "k_filter2.cuh"
 #include "k_filter3.cuh"
 #include "k_filter5.cuh"
+#include "k_filter5t.cuh"
 #include "k_select.cuh"
 #include "k_sumthreshold.cuh"
 
@@ -56,8 +57,9 @@ static int dev_bg_work_alloc(tc_context *c, int64_t N, bool two_axes, BgWork *w)
     TC_TRY(tc_alloc(c, N, &w->fl_FT));
     w->v_FT = w->w_FT = nullptr;
     if (two_axes) {
-        TC_TRY(tc_alloc(c, N, &w->v_FT));
-        TC_TRY(tc_alloc(c, N, &w->w_FT));
+        // one allocation: the TMA form of the second-axis filter addresses the pair as one 3-D tensor
+        TC_TRY(tc_alloc(c, 2 * N, &w->v_FT));
+        w->w_FT = w->v_FT + N;
     }
     return TC_OK;
 }
@@ -131,7 +133,8 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
             // the lane-per-chain kernels can leave their output line-contiguous, i.e. in (T,F)
             b.data2 = data_TF;
             if (want_TF && got_TF) { b.out_transposed = 1; *got_TF = 1; }
-            if (b5_1) TC_TRY(launch_box_filter5(c, b));
+            if (b5_1 && b5t_supported(c, b)) TC_TRY(launch_box_filter5t(c, b));
+            else if (b5_1) TC_TRY(launch_box_filter5(c, b));
             else TC_TRY(launch_box_filter2(c, b));
         } else if (tplb) {
             // thread per line: the output is sample-major for this axis, i.e. (F,T)

@@ -92,3 +92,50 @@ def test_window_statistics_container():
     assert c._counts_per_ant["x"] == 5 and c._size_per_ant["x"] == 20
     assert c._counts_per_ddid[0].tolist() == [0, 1, 2, 3]
     assert a._counts_per_ant["x"] == 2
+
+
+def test_hoisted_reciprocal_division_is_exact_over_its_guard_range():
+    """B2Div (csrc/k_filter2.cuh): x / d by q0 = x * rinv, rem = fma(-q0, d, x), q = fma(rem, rinv, q0)
+    with rinv = the refined reciprocal of d = float32(2r + 1) ** 4.  The kernels use it for
+    |x| in [2^-87, 2^123) (and zero) and the plain division elsewhere; here the sequence is
+    replayed in exact rational arithmetic (every fma rounded once to float32) and compared
+    with the correctly rounded quotient, over the whole guarded range incl. its ends."""
+    import random
+    from fractions import Fraction as Fr
+
+    def f32(fr):
+        if fr == 0:
+            return Fr(0)
+        s = 1 if fr > 0 else -1
+        a = abs(fr)
+        e = a.numerator.bit_length() - a.denominator.bit_length()
+        if Fr(2) ** e > a:
+            e -= 1
+        if Fr(2) ** (e + 1) <= a:
+            e += 1
+        e = max(e, -126)
+        q = Fr(2) ** (e - 23)
+        m = a / q
+        fl = m.numerator // m.denominator
+        rem = m - fl
+        if rem > Fr(1, 2) or (rem == Fr(1, 2) and fl % 2 == 1):
+            fl += 1
+        return s * fl * q
+
+    def fma(a, b, c):
+        return f32(a * b + c)
+
+    rnd = random.Random(11)
+    for r in (4, 8, 43, 127, 277):
+        d32 = np.float32(2 * r + 1)
+        d32 = np.float32(d32 * d32)
+        d32 = np.float32(d32 * d32)
+        d = Fr(float(d32))
+        r0 = f32(1 / d)
+        rinv = fma(r0, fma(-d, r0, Fr(1)), r0)
+        for i in range(1500):
+            ex = (-87, 122, rnd.randint(-87, -30), rnd.randint(-30, 60), rnd.randint(60, 122))[i % 5]
+            x = Fr(rnd.randint(2 ** 23, 2 ** 24 - 1)) * Fr(2) ** (ex - 23)
+            q0 = f32(x * rinv)
+            q = fma(fma(-q0, d, x), rinv, q0)
+            assert q == f32(x / d), (r, ex)

@@ -627,6 +627,22 @@ def test_stokes(backend, stokes):
     w[2::3, :, 1] = 0
     got, want = tb.polarised_intensity(w, pol), oracle.polarised_intensity(w, pol)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # results that sit exactly on (or within a few float64 ulps of) a float32 rounding midpoint: the
+    # interval shortcut of the kernel must notice and replay the exact sequence.  With XY = YX = 0 the
+    # polarised intensity is |Q| = |XX - YY| / 2 (or whatever single term the set keeps): operands are
+    # chosen so that it is 2^24 + 1 + k ulp(float64), k = -3..3.
+    if len(stokes) == 4:
+        m = np.zeros((16, 1, 4), np.complex64)
+        m[:, 0, 0] = np.float32(2.0 ** 25)
+        m[:, 0, 3] = -np.float32(2.0) * (1 + np.arange(16, dtype=np.float32) * np.float32(2.0 ** -23))
+        m[8:, 0, 0] *= np.float32(2.0 ** -40)
+        m[8:, 0, 3] *= np.float32(2.0 ** -40)
+        m[3, 0, :] = 0                       # all-zero sample
+        m[5, 0, 1] = np.nan                  # non-finite term
+        for fn_t, fn_o, args in ((tb.polarised_intensity, oracle.polarised_intensity, (pol,)),
+                                 (tb.unpolarised_intensity, oracle.unpolarised_intensity, (unpol, pol))):
+            got, want = fn_t(m, *args), fn_o(m, *args)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     with pytest.raises(ValueError):
         tb.unpolarised_intensity(v, (), pol)
     with pytest.raises(ValueError):

@@ -244,8 +244,8 @@ __device__ __forceinline__ double stokes_abs(const float2 *v, const StokesTerms 
 }
 
 // sqrt(sum |pol term|^2), or (sum |unpol term|) - that, in float64 (stokes.py:132-153, 196-208)
-__device__ __forceinline__ double stokes_intensity(const float2 *v, const StokesTerms &pol, const StokesTerms &unpol,
-                                                   int with_unpol)
+__device__ __forceinline__ double stokes_intensity_exact(const float2 *v, const StokesTerms &pol, const StokesTerms &unpol,
+                                                         int with_unpol)
 {
     double p = 0.0;
     for (int k = 0; k < pol.n; k++) {
@@ -259,6 +259,70 @@ __device__ __forceinline__ double stokes_intensity(const float2 *v, const Stokes
         r = __dadd_rn(u, -r);
     }
     return r;
+}
+
+// float32 bits of a FINITE value -> the double x * 2^-896 (exact; same trick as the box filter's
+// accumulators, k_filter2.cuh): one IMAD.WIDE and a mask on the integer pipes instead of a conversion
+// on the 16-lane XU pipe, the 2^896 rides on the coefficient that multiplies it
+__device__ __forceinline__ double ew_spread(float x)
+{
+#ifndef TC_EMU
+    int hi, lo;
+    asm("{\n\t.reg .s64 w;\n\tmul.wide.s32 w, %2, 536870912;\n\tmov.b64 {%1, %0}, w;\n\t}"
+        : "=r"(hi), "=r"(lo) : "r"(__float_as_int(x)));
+    return __hiloint2double(hi & (int)0x8fffffff, lo);
+#else
+    return (double)x * 0x1p-896;
+#endif
+}
+
+__device__ __forceinline__ void stokes_term_fast(const float2 *v, const StokesTerms &t, int k, double *vr, double *vi)
+{
+    const float2 a = v[t.c1[k]], b = v[t.c2[k]];
+    const double s1 = t.s1[k] * 0x1p896, s2 = t.s2[k] * 0x1p896;
+    const double re = s1 * ew_spread(a.x) + s2 * ew_spread(b.x);
+    const double im = s1 * ew_spread(a.y) + s2 * ew_spread(b.y);
+    *vr = t.ar[k] * re - t.ai[k] * im;
+    *vi = t.ar[k] * im + t.ai[k] * re;
+}
+
+// The float32 the reference stores.  The exact sequence above costs three double hypots (a square
+// root and a division each) and a square root per sample and keeps the kernel on the FP64 pipe at
+// 28 % of the HBM roofline.  |a|^2 of a correctly-replayed hypot differs from re^2 + im^2 by a few
+// ulps of a double, so the sum of squares -- and with it the float64 result -- is known to within
+// 2^-49 relative without any hypot; only when the two ends of that interval round to different
+// float32 values (probability ~2^-27 per sample) is the exact sequence replayed.  Same bits out.
+__device__ __forceinline__ float stokes_intensity(const float2 *v, const StokesTerms &pol, const StokesTerms &unpol,
+                                                  int with_unpol, int ncorr)
+{
+    // NaN / Inf anywhere: the exact sequence (x * 0 is NaN exactly for those)
+    float chk = 0.f;
+    for (int cidx = 0; cidx < ncorr && cidx < 8; cidx++) chk = fmaf(v[cidx].x, 0.f, fmaf(v[cidx].y, 0.f, chk));
+    if (chk != 0.f) return (float)stokes_intensity_exact(v, pol, unpol, with_unpol);
+    double p = 0.0;
+    for (int k = 0; k < pol.n; k++) {
+        double vr, vi;
+        stokes_term_fast(v, pol, k, &vr, &vi);
+        p += __fma_rn(vr, vr, vi * vi);
+    }
+    double r = __dsqrt_rn(p), scale = r;
+    if (with_unpol) {
+        double u = 0.0;
+        for (int k = 0; k < unpol.n; k++) {
+            double vr, vi;
+            stokes_term_fast(v, unpol, k, &vr, &vi);
+            u += __dsqrt_rn(__fma_rn(vr, vr, vi * vi));
+        }
+        scale = u > r ? u : r;
+        r = u - r;
+    }
+    if (scale == 0.0) return 0.0f;          // every term exactly zero: so is the reference's result
+    const double e = scale * 0x1p-46;
+    const float lo = (float)(r - e), hi = (float)(r + e);
+    // !(lo == hi) also catches NaN (non-finite input) and sends it down the exact path
+    if (!(lo == hi) || !(scale > 0x1p-400 && scale < 0x1p400))
+        return (float)stokes_intensity_exact(v, pol, unpol, with_unpol);
+    return lo;
 }
 
 __global__ void __launch_bounds__(256)
@@ -276,7 +340,7 @@ k_stokes(const float2 *__restrict__ vis, int64_t n, int ncorr, StokesTerms pol,
     } else {
         for (int c = 0; c < ncorr && c < 8; c++) v[c] = src[c];
     }
-    out[i] = make_float2((float)stokes_intensity(v, pol, unpol, with_unpol), 0.0f);
+    out[i] = make_float2(stokes_intensity(v, pol, unpol, with_unpol, ncorr), 0.0f);
 }
 
 // ----------------------------------------------------------------------------

@@ -148,61 +148,87 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     const unsigned jsmax = dok ? (unsigned)n : 0u;
     B2Div dv;
     dv.init(a.div);
-    auto drain = [&](int buf) {
-        if ((unsigned)js < jsmax) {
-            const uint4 *row = stage + (buf * GQ + dq) * B5_STAGE_ROW;
-            if (NARR == 1) {
-                const uint4 v = row[dl];
-                const unsigned y[4] = {v.x, v.y, v.z, v.w};
-                float o[4];
+    // The drain is split so that its arithmetic is straight-line code the compiler can interleave with the
+    // chain steps: drain_math runs the call-free division sequences on every lane and records whether an
+    // operand was outside the range where they are exact; drain_store redoes those lanes with the plain
+    // divisions (one warp vote; never taken on amplitude data) and stores.
+    // exact ranges: B2Div::fast for |x| in [2^-87, 2^123) or 0; b2_div_fast for quotients by d^4 in [2^-60, 2^60)
+    // (the value may be 0) -- which also pins the undivided sums inside the first range.
+    float o[4];
+    unsigned yraw[4];
+    bool dbad = false;
+    auto in_q_range = [](float q) { return __float_as_uint(q) - ((127u - 60u) << 23) < (120u << 23); };
+    auto drain_math = [&](int buf) {
+        const uint4 *row = stage + (buf * GQ + dq) * B5_STAGE_ROW;
+        if (NARR == 1) {
+            const uint4 v = row[dl];
+            yraw[0] = v.x; yraw[1] = v.y; yraw[2] = v.z; yraw[3] = v.w;
+            dbad = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
                 if (INTW) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) o[k] = dv.of_count(y[k]);
+                    o[k] = dv.of_count(yraw[k]);
                 } else {
-                    const bool safe = dv.safe(y[0]) && dv.safe(y[1]) && dv.safe(y[2]) && dv.safe(y[3]);
-                    if (safe) {
+                    o[k] = dv.fast(__uint_as_float(yraw[k]));
+                    dbad = dbad || !(yraw[k] == 0u || yraw[k] - (40u << 23) < (210u << 23));
+                }
+            }
+        } else {
+            const uint2 v = reinterpret_cast<const uint2 *>(row + dl)[dh];
+            const uint2 w = reinterpret_cast<const uint2 *>(row + 4 + dl)[dh];
+            yraw[0] = v.x; yraw[1] = v.y; yraw[2] = w.x; yraw[3] = w.y;
+            dbad = false;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) o[k] = dv.fast(__uint_as_float(y[k]));
-                    } else {
+            for (int k = 0; k < 2; k++) {
+                const float fv = dv.fast(__uint_as_float(yraw[k]));
+                const float fw = dv.fast(__uint_as_float(yraw[2 + k]));
+                dbad = dbad || !((fv == 0.f && yraw[k] == 0u) || in_q_range(fv)) || !((fw == 0.f && yraw[2 + k] == 0u) || in_q_range(fw));
+                if (MODE_OUT == FOUT_PAIR) {
+                    o[k] = fv;
+                    o[2 + k] = fw;
+                } else {
+                    o[k] = (fw == 0.f) ? NAN : b2_div_fast(fv, fw);
+                }
+            }
+        }
+    };
+    auto drain_store = [&]() {
+        const bool valid = (unsigned)js < jsmax;
+        if (!INTW && __ballot_sync(TC_FULL_MASK, dbad && valid) != 0u) {
+            if (dbad) {
+                if (NARR == 1) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) o[k] = dv(__uint_as_float(y[k]));
+                    for (int k = 0; k < 4; k++) o[k] = dv(__uint_as_float(yraw[k]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const float fv = dv(__uint_as_float(yraw[k]));
+                        const float fw = dv(__uint_as_float(yraw[2 + k]));
+                        if (MODE_OUT == FOUT_PAIR) {
+                            o[k] = fv;
+                            o[2 + k] = fw;
+                        } else {
+                            o[k] = (fw == 0.f) ? NAN : fv / fw;
+                        }
                     }
                 }
+            }
+        }
+        if (valid) {
+            if (NARR == 1) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) pv[(int64_t)k * omul] = o[k];
+            } else if (MODE_OUT == FOUT_PAIR) {
+                pv[0] = o[0]; pv[omul] = o[1];
+                pw[0] = o[2]; pw[omul] = o[3];
             } else {
-                const uint2 v = reinterpret_cast<const uint2 *>(row + dl)[dh];
-                const uint2 w = reinterpret_cast<const uint2 *>(row + 4 + dl)[dh];
-                const unsigned yv[2] = {v.x, v.y}, yw[2] = {w.x, w.y};
-                float fv[2], fw[2], res[2];
-                const bool safe = dv.safe(yv[0]) && dv.safe(yv[1]) && dv.safe(yw[0]) && dv.safe(yw[1]);
-                if (safe) {
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        fv[k] = dv.fast(__uint_as_float(yv[k]));
-                        fw[k] = dv.fast(__uint_as_float(yw[k]));
-                        res[k] = (fw[k] == 0.f) ? NAN : b2_div_fast(fv[k], fw[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        fv[k] = dv(__uint_as_float(yv[k]));
-                        fw[k] = dv(__uint_as_float(yw[k]));
-                        res[k] = (fw[k] == 0.f) ? NAN : fv[k] / fw[k];
-                    }
+                if (MODE_OUT == FOUT_RESID) {
+                    const float2 d2 = *reinterpret_cast<const float2 *>(pd2);
+                    o[0] = fabsf(d2.x - o[0]);
+                    o[1] = fabsf(d2.y - o[1]);
                 }
-                if (MODE_OUT == FOUT_PAIR) {
-                    pv[0] = fv[0]; pv[omul] = fv[1];
-                    pw[0] = fw[0]; pw[omul] = fw[1];
-                } else {
-                    if (MODE_OUT == FOUT_RESID) {
-                        const float2 d2 = *reinterpret_cast<const float2 *>(pd2);
-                        res[0] = fabsf(d2.x - res[0]);
-                        res[1] = fabsf(d2.y - res[1]);
-                    }
-                    pv[0] = res[0];
-                    pv[omul] = res[1];
-                }
+                pv[0] = o[0];
+                pv[omul] = o[1];
             }
         }
         js += G;
@@ -232,9 +258,21 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
 
     const int niter = (n + r4 + G - 1) / G + 3;          // pass 3 finishes local group niter - 4 in the last iteration
     int pubv = GQ % nvec;
-    for (int g = 0;; g++) {
-        drain((g - 1) & 1);                              // what pass 3 staged in the previous iteration
-        if (g == niter) break;
+    // the leaving samples of the next iteration are loaded one iteration ahead whenever they are all older
+    // than the group the producer is writing (2r >= G); the entering ones only exist after the __syncwarp
+    const bool ahead = r2 >= G;
+    uint4 nxt[GQ];
+    auto load_leaving = [&](uint4 *dst) {
+        int rq = lv;
+#pragma unroll
+        for (int q = 0; q < GQ; q++) {
+            dst[q] = ring[rq * 32];
+            rq++; if (rq == nvec) rq = 0;
+        }
+        lv = rq;
+    };
+    if (ahead) load_leaving(nxt);
+    for (int g = 0; g < niter; g++) {
         publish(pubv);                                   // group g + 1 of the input
         pubv += GQ; if (pubv == nvec) pubv = 0;
         fetch(g + 2);
@@ -242,15 +280,14 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         uint4 e[GQ], nw[GQ];
 #pragma unroll
         for (int q = 0; q < GQ; q++) e[q] = ring[(ev + q) * 32];
-        {
-            int rq = lv;
+        if (ahead) {
 #pragma unroll
-            for (int q = 0; q < GQ; q++) {
-                nw[q] = ring[rq * 32];
-                rq++; if (rq == nvec) rq = 0;
-            }
-            lv = rq;
+            for (int q = 0; q < GQ; q++) nw[q] = nxt[q];
+            load_leaving(nxt);
+        } else {
+            load_leaving(nw);
         }
+        drain_math((g - 1) & 1);                         // what pass 3 staged in the previous iteration
         unsigned in[G], old[G], y[G];
 #pragma unroll
         for (int q = 0; q < GQ; q++) {
@@ -287,8 +324,11 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         for (int q = 0; q < GQ; q++)
             ydst[(yv + q) * ystride] = make_uint4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
         ev += GQ; if (ev == nvec) ev = 0;
+        drain_store();
         __syncwarp();
     }
+    drain_math((niter - 1) & 1);
+    drain_store();
 }
 
 // first axis of the 2-D masked filter: even blocks filter the values (float64 chains)

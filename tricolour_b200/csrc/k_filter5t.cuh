@@ -200,21 +200,13 @@ k_box5t(FilterArgs a, const __grid_constant__ B5TMaps maps)
             const uint2 w = reinterpret_cast<const uint2 *>(row + 4 + dl)[dh];
             const unsigned yv[2] = {v.x, v.y}, yw[2] = {w.x, w.y};
             float fv[2], fw[2], res[2];
-            const bool safe = dv.safe(yv[0]) && dv.safe(yv[1]) && dv.safe(yw[0]) && dv.safe(yw[1]);
-            if (safe) {
+            // one path for every sample: a group-level fast / plain split diverges wherever flagged
+            // regions make some weights tiny, and then costs both
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    fv[k] = dv.fast(__uint_as_float(yv[k]));
-                    fw[k] = dv.fast(__uint_as_float(yw[k]));
-                    res[k] = (fw[k] == 0.f) ? NAN : b2_div_fast(fv[k], fw[k]);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    fv[k] = dv(__uint_as_float(yv[k]));
-                    fw[k] = dv(__uint_as_float(yw[k]));
-                    res[k] = (fw[k] == 0.f) ? NAN : fv[k] / fw[k];
-                }
+            for (int k = 0; k < 2; k++) {
+                fv[k] = dv(__uint_as_float(yv[k]));
+                fw[k] = dv(__uint_as_float(yw[k]));
+                res[k] = (fw[k] == 0.f) ? NAN : fv[k] / fw[k];
             }
             if (MODE_OUT == FOUT_RESID) {
                 const float2 d2 = *reinterpret_cast<const float2 *>(d2_p + 64 * par + dl * 16 + ds);

@@ -21,6 +21,26 @@ k_fill_windows(float2 *__restrict__ vis_win, u8 *__restrict__ flag_win, int64_t 
     if (flag_win) flag_win[i] = 1;
 }
 
+// the same defaults for the (baseline, time) slots no row writes: `slots` holds bl * ntime + t,
+// a slot is ncorr runs of nchan samples.  Everything else is overwritten by the pack itself, so
+// a window that every row covers is written once instead of twice.
+__global__ void __launch_bounds__(256)
+k_fill_slots(const int32_t *__restrict__ slots, int64_t nslots, int ncorr, int ntime, int nchan,
+             float2 *__restrict__ vis_win, u8 *__restrict__ flag_win)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)ncorr * nchan;
+    if (g >= nslots * per) return;
+    const int64_t s = g / per;
+    const int64_t rem = g - s * per;
+    const int cc = (int)(rem / nchan), f = (int)(rem - (int64_t)cc * nchan);
+    const int slot = slots[s];
+    const int bl = slot / ntime, t = slot - bl * ntime;
+    const int64_t dst = (((int64_t)bl * ncorr + cc) * ntime + t) * nchan + f;
+    if (vis_win) vis_win[dst] = make_float2(NAN, NAN);
+    if (flag_win) flag_win[dst] = 1;
+}
+
 __global__ void __launch_bounds__(256)
 k_pack(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ row_t, int64_t nrow,
        const float2 *__restrict__ vis, const u8 *__restrict__ flags, int nchan, int ncorr,
@@ -254,7 +274,7 @@ k_stokes_pack(const int32_t *__restrict__ row_bl, const int32_t *__restrict__ ro
         any = any ? 1 : 0;
     }
     const int64_t dst = ((int64_t)bl * ntime + t) * nchan + f;
-    vis_win[dst] = make_float2((float)stokes_intensity(v, pol, unpol, with_unpol), 0.0f);
+    vis_win[dst] = make_float2(stokes_intensity(v, pol, unpol, with_unpol, ncorr), 0.0f);
     flag_win[dst] = any;
 }
 

@@ -1465,8 +1465,11 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         // select; blocks of all other ranges exit at once
         ChunkSelectArgs f = a;
         f.todo = todo;
-        if (max_range > 8 * TC_SEL_SLICE) {
+        if (max_range > 64 * TC_SEL_SLICE) {
             // very long ranges: one block per range would crawl, use the sliced radix select
+            // (eight launches; below that size the few ranges that need it are cheaper in one launch
+            // whose other blocks exit at once -- 40 selects per strategy pass make the difference
+            // between ~1100 and ~850 launches per 12-task step)
             TC_TRY(launch_chunk_select_multi(c, f, nranges, max_range, false));
             goto fallback_done;
         }

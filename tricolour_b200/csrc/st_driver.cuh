@@ -47,6 +47,15 @@ static int dev_make_ranges(tc_context *c, int64_t np, int64_t T, int64_t Fa, con
     return TC_OK;
 }
 
+// device tables that depend only on the batch shape and the chunk boundaries: built once per plane
+// batch (tc_sum_threshold) instead of once per pass
+struct PassTables {
+    int64_t np; int T, Fa, nce;
+    int64_t *slo, *shi, smax;      // (plane, chunk) ranges of the spectra (T = 1)
+    int64_t *rlo, *rhi, rmax;      // (plane, chunk) ranges of the planes in (F,T) order
+    int64_t *d_ce, *d_tce;         // frequency chunk ends; {0, T}
+};
+
 struct BgWork {
     u8 *fl_FT;            // working copy of the flags (gets modified), (plane, chan, time)
     float *v_FT, *w_FT;   // time-filtered value / weight, already in (plane, chan, time)
@@ -98,7 +107,7 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     // (measured on B200, profiles/r02_filter_probe.txt: first axis from r = 37, where the thread-per-line
     // weight chains stop; second axis up to r ~ 200, beyond which the longer rings cost occupancy)
     static const int b5_a_minr = tpl_env_int("TC_B5_A_MINR", 37), b5_b_minr = tpl_env_int("TC_B5_B_MINR", 1);
-    static const int b5_b_maxr = tpl_env_int("TC_B5_B_MAXR", 200);
+    static const int b5_b_maxr = tpl_env_int("TC_B5_B_MAXR", 12);
     probe.n = T; probe.r = (int)r0; probe.data = data_FT; probe.flags = w.fl_FT;
     const bool b5_0 = r0 >= b5_a_minr && r0 > 0 && b5_supported(c, probe);
     probe.n = Fa; probe.r = (int)r1; probe.data = w.v_FT; probe.win = w.w_FT; probe.flags = nullptr;
@@ -232,7 +241,7 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
                              const float *d_FT, const u8 *fl_TF, const u8 *fl_FT,
                              const u8 *fl2_TF, const int64_t *windows, const double *tf,
                              const float *scale, int nwin, double nsigma, const int64_t *ce,
-                             int nce, u8 *out /* TF for axis 0, FT for axis 1 */)
+                             int nce, u8 *out /* TF for axis 0, FT for axis 1 */, int64_t *d_ce_cached = nullptr)
 {
     TC_REQUIRE(nwin > 0, "zero-size array to reduction operation maximum which has no identity");
     TC_REQUIRE(nwin <= TC_MAX_WINDOWS, "at most %d SumThreshold windows are supported", TC_MAX_WINDOWS);
@@ -255,8 +264,8 @@ static int dev_sum_threshold(tc_context *c, int64_t np, int T, int Fa, int axis,
     }
     if (nchunks <= 0 || np == 0) return TC_OK;
     tc_mark mark = tc_arena_mark(c);
-    int64_t *d_ce = nullptr;
-    TC_TRY(dev_upload_i64(c, ce, (size_t)nce, &d_ce));
+    int64_t *d_ce = d_ce_cached;
+    if (!d_ce) TC_TRY(dev_upload_i64(c, ce, (size_t)nce, &d_ce));
     int64_t ninner = axis == 0 ? Fa : T;  // lines per plane
     int64_t nlines = np * ninner;
     float *thr = nullptr;
@@ -355,12 +364,24 @@ static int dev_combine_flags(tc_context *c, int64_t np, int T, int Fa, int F, in
     return TC_OK;
 }
 
+static int dev_pass_tables(tc_context *c, const tc_st_params *p, int64_t np, int T, int F, PassTables *t)
+{
+    const int avg = (int)p->average_freq;
+    t->np = np; t->T = T; t->Fa = (F + avg - 1) / avg; t->nce = p->nchunk_ends;
+    TC_TRY(dev_make_ranges(c, np, 1, t->Fa, p->freq_chunk_ends, t->nce, &t->slo, &t->shi, &t->smax));
+    TC_TRY(dev_make_ranges(c, np, T, t->Fa, p->freq_chunk_ends, t->nce, &t->rlo, &t->rhi, &t->rmax));
+    TC_TRY(dev_upload_i64(c, p->freq_chunk_ends, (size_t)t->nce, &t->d_ce));
+    const int64_t tce[2] = {0, T};
+    TC_TRY(dev_upload_i64(c, tce, 2, &t->d_tce));
+    return TC_OK;
+}
+
 // ----------------------------------------------------------------------------
 // one _get_flags_impl pass over np planes
 // ----------------------------------------------------------------------------
 static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *vis, int vis_kind,
                               const u8 *in_flags, int64_t np, int T, int F, u8 *out_flags,
-                              u8 *iter_flags_accum)
+                              u8 *iter_flags_accum, const PassTables *tab = nullptr)
 {
     const int avg = (int)p->average_freq;
     const int Fa = (F + avg - 1) / avg;
@@ -414,15 +435,19 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
         TC_TRY(launch_line_median(c, m, T));
     }
     // spectrum background (flagging.py:945-949) and its SumThreshold (950-952)
-    int64_t *slo, *shi, smax;
-    TC_TRY(dev_make_ranges(c, np, 1, Fa, p->freq_chunk_ends, nce, &slo, &shi, &smax));
+    PassTables local;
+    if (!tab) {
+        TC_TRY(dev_pass_tables(c, p, np, T, F, &local));
+        tab = &local;
+    }
+    int64_t *slo = tab->slo, *shi = tab->shi, smax = tab->smax;
     float *spec_res;
     TC_TRY(tc_alloc(c, np * (int64_t)Fa, &spec_res));
     TC_TRY(dev_background2d(c, np, 1, Fa, spec_data, spec_data, spec_fl, spec_fl, iters, p->radii_spec,
                             p->background_reject, slo, shi, nchunks, smax, spec_bg, spec_res, spec_data));
     TC_TRY(dev_sum_threshold(c, np, 1, Fa, 1, spec_res, spec_res, spec_fl, spec_fl, nullptr,
                              p->windows_freq, p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
-                             p->freq_chunk_ends, nce, spec_out));
+                             p->freq_chunk_ends, nce, spec_out, tab->d_ce));
     // flags |= spec_flags (flagging.py:954), both layouts
     if ((Fa & 15) == 0 && (T & 15) == 0 && T <= 65535 && np <= 65535) {
         // flag bytes are 0/1 (k_prep wrote them): OR whole vectors, in both layouts
@@ -443,8 +468,7 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     // 2-D background (flagging.py:957-961)
     float *bg_FT, *dres_TF;
     TC_TRY(tc_alloc(c, N, &bg_FT)); TC_TRY(tc_alloc(c, N, &dres_TF));
-    int64_t *rlo, *rhi, rmax;
-    TC_TRY(dev_make_ranges(c, np, T, Fa, p->freq_chunk_ends, nce, &rlo, &rhi, &rmax));
+    int64_t *rlo = tab->rlo, *rhi = tab->rhi, rmax = tab->rmax;
     // background and data -= background (flagging.py:957-962), in both layouts
     TC_TRY(dev_background2d(c, np, T, Fa, data_TF, data_FT, fl_TF, fl_FT, iters, p->radii_2d,
                             p->background_reject, rlo, rhi, nchunks, rmax, bg_FT, dres_TF, data_TF));
@@ -456,11 +480,11 @@ static int dev_get_flags_pass(tc_context *c, const tc_st_params *p, const void *
     TC_TRY(tc_alloc(c, N, &time_TF)); TC_TRY(tc_alloc(c, N, &freq_FT)); TC_TRY(tc_alloc(c, N, &freq_TF));
     int64_t tce[2] = {0, T};
     TC_TRY(dev_sum_threshold(c, np, T, Fa, 0, dres_TF, dres_FT, fl_TF, fl_FT, nullptr, p->windows_time,
-                             p->tf_time, p->scale_time, p->nwin_time, p->outlier_nsigma, tce, 2, time_TF));
+                             p->tf_time, p->scale_time, p->nwin_time, p->outlier_nsigma, tce, 2, time_TF, tab->d_tce));
     // flags |= time_flags; SumThreshold along frequency (flagging.py:967-969)
     TC_TRY(dev_sum_threshold(c, np, T, Fa, 1, dres_TF, dres_FT, fl_TF, fl_FT, time_TF, p->windows_freq,
                              p->tf_freq, p->scale_freq, p->nwin_freq, p->outlier_nsigma,
-                             p->freq_chunk_ends, nce, freq_FT));
+                             p->freq_chunk_ends, nce, freq_FT, tab->d_ce));
     TC_TRY(launch_transpose<u8>(c, freq_FT, freq_TF, np, Fa, T));
 
     // _combine_flags + _unaverage_freq + final isnan OR

@@ -271,9 +271,11 @@ int tc_sum_threshold(tc_context *c, const tc_st_params *p, const void *vis, int 
         TC_TRY(launch_norm_flags(c, dfl, iter_flags, n));
         c->launches++;
         TC_KERNEL_CHECK();
+        PassTables tab;
+        TC_TRY(dev_pass_tables(c, p, np, (int)T, (int)F, &tab));
         for (int it = 0; it < p->num_major_iterations; it++)
             TC_TRY(dev_get_flags_pass(c, p, dvis, vis_kind, iter_flags, np, (int)T, (int)F,
-                                      dout + p0 * T * F, iter_flags));
+                                      dout + p0 * T * F, iter_flags, &tab));
         tc_arena_release(c, mark);
     }
     return tc_stage_out_end(c, out, dout, (size_t)total, space);
@@ -403,6 +405,34 @@ static int upload_i32(tc_context *c, const int32_t *h, size_t n, int32_t **d)
     return TC_OK;
 }
 
+// window defaults before a pack: only the (baseline, time) slots that no row writes
+static int pack_fill(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow, int64_t nbl,
+                     int64_t ntime, int64_t ncorr_win, int64_t nchan, float2 *dvw, u8 *dfw)
+{
+    const int64_t nslot = nbl * ntime, nwin = nslot * ncorr_win * nchan;
+    if (nwin == 0) return TC_OK;
+    if (nslot >= ((int64_t)1 << 31) || TC_ENV_FLAG("TC_PACK_FULL_FILL")) {
+        TC_LAUNCH_NOSYNC(k_fill_windows, tc_blocks_for(nwin, 256), 256, 0, c->stream, dvw, dfw, nwin);
+        c->launches++;
+        return TC_OK;
+    }
+    std::vector<u8> covered((size_t)nslot, 0);
+    for (int64_t r = 0; r < nrow; r++)
+        if (row_bl[r] >= 0) covered[(size_t)row_bl[r] * ntime + row_t[r]] = 1;
+    std::vector<int32_t> open_slots;
+    for (int64_t s = 0; s < nslot; s++)
+        if (!covered[(size_t)s]) open_slots.push_back((int32_t)s);
+    if (open_slots.empty()) return TC_OK;
+    int32_t *dslots;
+    TC_TRY(tc_alloc(c, open_slots.size(), &dslots));
+    TC_TRY(tc_upload_small(c, open_slots.data(), open_slots.size() * sizeof(int32_t), dslots));
+    const int64_t work = (int64_t)open_slots.size() * ncorr_win * nchan;
+    TC_LAUNCH_NOSYNC(k_fill_slots, tc_blocks_for(work, 256), 256, 0, c->stream, dslots, (int64_t)open_slots.size(),
+                     (int)ncorr_win, (int)ntime, (int)nchan, dvw, dfw);
+    c->launches++;
+    return TC_OK;
+}
+
 int tc_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t nrow, const void *vis,
             const uint8_t *flags, int64_t nchan, int64_t ncorr, int64_t ntime, int64_t nbl,
             void *vis_win, uint8_t *flag_win, int fill, int space)
@@ -432,10 +462,7 @@ int tc_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, int64_t 
             TC_CUDA(cudaMemcpyAsync(dfw, flag_win, (size_t)nwin, cudaMemcpyHostToDevice, c->stream));
     }
     tc_prof_begin(c, TCP_PACK);
-    if (fill && nwin) {
-        TC_LAUNCH_NOSYNC(k_fill_windows, tc_blocks_for(nwin, 256), 256, 0, c->stream, dvw, dfw, nwin);
-        c->launches++;
-    }
+    if (fill && nwin) TC_TRY(pack_fill(c, row_bl, row_t, nrow, nbl, ntime, ncorr, nchan, dvw, dfw));
     if (nin) {
         bool c4 = ncorr == 4 && nchan % 4 == 0 && (((uintptr_t)dvis | (uintptr_t)dfl | (uintptr_t)dvw | (uintptr_t)dfw) & 15) == 0;
         if (c4) {
@@ -573,10 +600,7 @@ int tc_stokes_pack(tc_context *c, const int32_t *row_bl, const int32_t *row_t, i
         TC_CUDA(cudaMemcpyAsync(dfw, flag_win, (size_t)nwin, cudaMemcpyHostToDevice, c->stream));
     }
     tc_prof_begin(c, TCP_PACK);
-    if (fill && nwin) {
-        TC_LAUNCH_NOSYNC(k_fill_windows, tc_blocks_for(nwin, 256), 256, 0, c->stream, dvw, dfw, nwin);
-        c->launches++;
-    }
+    if (fill && nwin) TC_TRY(pack_fill(c, row_bl, row_t, nrow, nbl, ntime, 1, nchan, dvw, dfw));
     if (nin) {
         TC_LAUNCH_NOSYNC(k_stokes_pack, tc_blocks_for(nrow * nchan, 256), 256, 0, c->stream, dbl, dt, nrow, dvis, dfl,
                          (int)nchan, (int)ncorr, (int)ntime, pol, unpol, nunpol > 0 ? 1 : 0, dvw, dfw);

@@ -596,6 +596,26 @@ def test_uvcontsub_flagger(backend):
         tb.uvcontsub_flagger(vis, flags[:, :1])
 
 
+def test_sum_threshold_flagger_complex128_input(backend):
+    """complex128 visibilities with average_freq == 1: the amplitude is taken in float64 and rounded once to
+    float32, as the reference does (flagging.py:856-871) -- same flags as handing that float32 amplitude over;
+    with frequency averaging the dtype is refused"""
+    rs = np.random.RandomState(71)
+    shape = (2, 2, 32, 64)
+    v = (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)) * 3 + 10
+    v[0, 0, 3, 5] = np.nan
+    v[1, 1, 7, :] *= 8
+    fl = rs.uniform(size=shape) < 0.05
+    kw = dict(outlier_nsigma=6, background_iterations=2, num_major_iterations=2)
+    got = G.sum_threshold_flagger(v.astype(np.complex128), fl, **kw)
+    amp = np.abs(v).astype(np.float32)
+    want = oracle.sum_threshold_flagger(amp, fl, **kw)
+    assert_same(got, want, "complex128 input")
+    with pytest.raises(TypeError):
+        G.sum_threshold_flagger(v.astype(np.complex128), fl, average_freq=2, **kw)
+
+
+
 # ---------------------------------------------------------------- stokes ------
 @pytest.mark.parametrize('stokes', [['YX', 'XX', 'XY', 'YY'], ['XX', 'XY', 'YX', 'YY'],
                                     ['RR', 'RL', 'LR', 'LL'], ['RL', 'RR', 'LL', 'LR']])

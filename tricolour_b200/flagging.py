@@ -328,8 +328,15 @@ def _vis_for_st(vis, average_freq):
     if v.dtype == np.float64 and int(average_freq) == 1:
         # |x| rounded once to float32 either way (avg_data is float32, weight 1)
         return np.ascontiguousarray(v.astype(np.float32)), _cabi.VIS_FLOAT32
+    if v.dtype == np.complex128 and int(average_freq) == 1:
+        # the reference takes |x| in float64 (glibc hypot, as numpy's np.abs) and stores it in the
+        # float32 avg_data (flagging.py:856-871, weight 1): the same single rounding on the host;
+        # NaN parts give a NaN amplitude, which the kernels treat like isnan(vis)
+        amp = np.abs(v)
+        amp[np.isnan(v.real) | np.isnan(v.imag)] = np.nan
+        return np.ascontiguousarray(amp.astype(np.float32)), _cabi.VIS_FLOAT32
     raise TypeError("sum_threshold supports complex64 / float32 visibilities "
-                    "(float64 only with average_freq == 1), got %s" % v.dtype)
+                    "(float64 / complex128 only with average_freq == 1), got %s" % v.dtype)
 
 
 def _run_sum_threshold(plan, vis3, flags3):

@@ -669,8 +669,37 @@ def ours(args):
                                       "flagged_final": int(red1._counts_per_field["synthetic"]),
                                       "size": int(red1._size_per_field["synthetic"])}
 
-    # ---- a lightly flagged workload beside the default one (config 1)
     extra = {}
+    # ---- config 0: the same call from a pool of host threads, one window each (how dask's
+    # ThreadPool drives the np_* functions, app.py:266-271): every thread has its own context and
+    # stream, the latency-bound launch chains of different windows overlap on the device
+    if args.config == 0 and not args.no_e2e and world == 1:
+        from concurrent.futures import ThreadPoolExecutor
+        import tricolour_b200 as tb
+        nthreads = 16
+        rounds = max(2, min(args.steps, 4))
+        wins = [(w.hv.copy(), w.hf.copy()) for _ in range(nthreads)]
+
+        def one(i):
+            return tb.sum_threshold_flagger(wins[i][0], wins[i][1], **w.kw3)
+
+        with ThreadPoolExecutor(nthreads) as pool:
+            ref_out = list(pool.map(one, range(nthreads)))             # warm-up: contexts, arenas
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(rounds):
+                outs = list(pool.map(one, range(nthreads)))
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+        same = all(np.array_equal(o, ref_out[0]) for o in outs)
+        extra["concurrent_windows"] = {
+            "value": nthreads * rounds * w.nvis / dtc / 1e9, "unit": "GVis/s", "host_threads": nthreads,
+            "windows": nthreads * rounds, "identical_outputs": bool(same),
+            "what": "sum_threshold_flagger(numpy window) called from %d host threads at once, host buffers in and "
+                    "out (the way dask's ThreadPool calls it); the single-window figures above are latency-bound"
+                    % nthreads}
+
+    # ---- a lightly flagged workload beside the default one (config 1)
     if args.config == 1 and not args.no_light:
         del w.vis, w.flags
         torch.cuda.empty_cache()

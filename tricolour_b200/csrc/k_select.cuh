@@ -671,20 +671,18 @@ __device__ __forceinline__ float cs_value(const ChunkSelectArgs &a, int64_t i, f
     return x;
 }
 
-__global__ void __launch_bounds__(1024)
-k_chunk_select(ChunkSelectArgs a)
+// Exact median of the keys of [lo, hi) that take part (unflagged and, with skip_nan, not NaN):
+// three 11/11/10-bit radix passes over the range itself, histogram in shared memory, the digit
+// holding the wanted rank found by all threads together (thread t owns 2048 / blockDim.x
+// neighbouring bins).  Every thread of the block calls it (128 ... 1024 threads) and gets the
+// result.  hist: 2048 words, s_wsum: 32 words, s_scal: 4 words of shared memory.
+__device__ __forceinline__ double block_range_median(const ChunkSelectArgs &a, int64_t lo, int64_t hi, float sub,
+                                                     uint32_t *hist, uint32_t *s_wsum, uint32_t *s_scal)
 {
-    __shared__ uint32_t hist[TC_SEL_BINS];
-    __shared__ uint32_t s_prefix, s_remaining, s_total, s_best;
-    __shared__ double s_thr;
-    if (a.todo && !a.todo[blockIdx.x]) return;  // fallback launch: only ranges whose bracket missed
-    const int64_t lo = a.range_lo[blockIdx.x], hi = a.range_hi[blockIdx.x];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const float sub = a.sub ? (float)a.sub[blockIdx.x] : 0.0f;
-
+    const int per = TC_SEL_BINS / nt;
     // digit layout over the 32-bit key: [31:21] [20:10] [9:0]
-    uint32_t prefix = 0, himask = 0;
-    uint32_t remaining = 0, total = 0;
+    uint32_t prefix = 0, himask = 0, remaining = 0, total = 0;
     for (int pass = 0; pass < 3; pass++) {
         const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
         const uint32_t dmask = pass == 2 ? 1023u : 2047u;
@@ -707,54 +705,74 @@ k_chunk_select(ChunkSelectArgs a)
             hist_add_agg(hist, bin, act);
         }
         __syncthreads();
-        if (tid == 0) {
-            if (pass == 0) {
-                uint32_t t = 0;
-                for (int b = 0; b < TC_SEL_BINS; b++) t += hist[b];
-                s_total = t;
-                s_remaining = t >> 1;
+        const uint32_t *mine = hist + tid * per;
+        uint32_t sum = 0;
+        for (int q = 0; q < per; q++) sum += mine[q];
+        uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+            if ((tid & 31) >= o) inc += v;
+        }
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t woff = 0, all = 0;
+        for (int w = 0; w < (nt >> 5); w++) {
+            const uint32_t ws = s_wsum[w];
+            if (w < (tid >> 5)) woff += ws;
+            all += ws;
+        }
+        if (pass == 0) { total = all; remaining = all >> 1; }
+        if (total == 0) break;                        // uniform: every thread sees the same total
+        const uint32_t excl = woff + inc - sum;
+        if (remaining >= excl && remaining < excl + sum) {
+            uint32_t acc = excl, digit = tid * per;
+            for (int q = 0; q < per; q++) {
+                const uint32_t hq = mine[q];
+                if (remaining < acc + hq) { digit = tid * per + q; break; }
+                acc += hq;
             }
-            uint32_t rem = s_remaining, acc = 0;
-            uint32_t digit = 0;
-            if (s_total > 0) {
-                for (uint32_t b = 0; b <= dmask; b++) {
-                    if (rem < acc + hist[b]) { digit = b; break; }
-                    acc += hist[b];
-                }
-                s_remaining = rem - acc;
-            }
-            s_prefix = prefix | (digit << shift);
+            s_scal[0] = prefix | (digit << shift);
+            s_scal[1] = remaining - acc;
         }
         __syncthreads();
-        prefix = s_prefix;
-        remaining = s_remaining;
-        total = s_total;
+        prefix = s_scal[0];
+        remaining = s_scal[1];
         himask |= dmask << shift;
-        if (total == 0) break;
+        __syncthreads();
     }
-    double med;
-    if (total == 0) {
-        med = NAN;
-    } else {
-        float upper = key2f(prefix), lower = upper;
-        if (!(total & 1u) && remaining == 0) {
-            if (tid == 0) s_best = 0;
-            __syncthreads();
-            uint32_t best = 0;
-            for (int64_t i = lo + tid; i < hi; i += nt) {
-                if (a.flags[i]) continue;
-                float x = cs_value(a, i, sub);
-                if (a.skip_nan && x != x) continue;
-                uint32_t k = f2key(x);
-                if (k < prefix && k > best) best = k;
-            }
-            best = warp_max_u(best);
-            if ((tid & 31) == 0) atomicMax(&s_best, best);
-            __syncthreads();
-            lower = key2f(s_best);
+    if (total == 0) return NAN;
+    float upper = key2f(prefix), lower = upper;
+    if (!(total & 1u) && remaining == 0) {
+        // even count and the upper middle key is the smallest of its value: the lower one is the
+        // largest key below it
+        if (tid == 0) s_scal[2] = 0;
+        __syncthreads();
+        uint32_t best = 0;
+        for (int64_t i = lo + tid; i < hi; i += nt) {
+            if (a.flags[i]) continue;
+            float x = cs_value(a, i, sub);
+            if (a.skip_nan && x != x) continue;
+            uint32_t k = f2key(x);
+            if (k < prefix && k > best) best = k;
         }
-        med = median_from_pair(lower, upper, (int)total);
+        best = warp_max_u(best);
+        if ((tid & 31) == 0) atomicMax(&s_scal[2], best);
+        __syncthreads();
+        lower = key2f(s_scal[2]);
     }
+    return median_from_pair(lower, upper, (int)total);
+}
+
+__global__ void __launch_bounds__(1024)
+k_chunk_select(ChunkSelectArgs a)
+{
+    __shared__ uint32_t hist[TC_SEL_BINS];
+    __shared__ uint32_t s_wsum[32], s_scal[4];
+    if (a.todo && !a.todo[blockIdx.x]) return;  // fallback launch: only ranges whose bracket missed
+    const int64_t lo = a.range_lo[blockIdx.x], hi = a.range_hi[blockIdx.x];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float sub = a.sub ? (float)a.sub[blockIdx.x] : 0.0f;
+    const double med = block_range_median(a, lo, hi, sub, hist, s_wsum, s_scal);
     if (a.medians && tid == 0) a.medians[blockIdx.x] = med;
     if (a.medbuf && tid == 0) a.medbuf[blockIdx.x] = med;
     if (a.mode == CS_REPORT || a.todo) return;
@@ -769,7 +787,6 @@ k_chunk_select(ChunkSelectArgs a)
     // CS_UVCONTSUB
     if (a.uv_unflagged[blockIdx.x] == 0) return;  // fully flagged plane: untouched
     float thr = a.uv_sigma * (float)med;          // float32 product (NEP 50)
-    (void)s_thr;
     for (int64_t i = lo + tid; i < hi; i += nt) {
         bool nf = a.resid[i] > thr;               // false for NaN on either side
         if (a.uv_replace) a.flags[i] = nf ? 1 : 0;
@@ -930,15 +947,11 @@ k_sel_finish(ChunkSelectArgs a, SelState *__restrict__ st, int nranges)
     if (a.medians) a.medians[range] = med;
 }
 
-__global__ void __launch_bounds__(1024)
-k_sel_update(ChunkSelectArgs a)
+// flags of [lo, hi) from the range's median: CS_BACKGROUND flags |= resid > median * thr_mult (float64),
+// CS_UVCONTSUB the rule of flagging.py:1056-1071.  Called by every thread of a block.
+__device__ __forceinline__ void sel_update_span(const ChunkSelectArgs &a, int range, double med, int64_t lo, int64_t hi,
+                                                bool allow_vec)
 {
-    const int range = blockIdx.y;
-    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
-    int64_t hi = lo + TC_SEL_SLICE;
-    if (hi > a.range_hi[range]) hi = a.range_hi[range];
-    if (lo >= hi) return;
-    const double med = a.medbuf[range];
     double thr;
     bool replace = false;
     if (a.mode == CS_BACKGROUND) {
@@ -952,7 +965,7 @@ k_sel_update(ChunkSelectArgs a)
     } else {
         return;
     }
-    const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
+    const bool vec = allow_vec && ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
     if (vec) {
         const int64_t n4 = (hi - lo) >> 2;
         for (int64_t q = threadIdx.x; q < n4; q += blockDim.x) {
@@ -980,6 +993,17 @@ k_sel_update(ChunkSelectArgs a)
             else if (nf) a.flags[i] = 1;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_sel_update(ChunkSelectArgs a)
+{
+    const int range = blockIdx.y;
+    const int64_t lo = a.range_lo[range] + (int64_t)blockIdx.x * TC_SEL_SLICE;
+    int64_t hi = lo + TC_SEL_SLICE;
+    if (hi > a.range_hi[range]) hi = a.range_hi[range];
+    if (lo >= hi) return;
+    sel_update_span(a, range, a.medbuf[range], lo, hi, true);
 }
 
 static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in, int64_t nranges, int64_t max_range,
@@ -1038,6 +1062,7 @@ static int launch_chunk_select_multi(tc_context *c, const ChunkSelectArgs &a_in,
 // The result is the same exact order statistic; only the visiting order differs.
 // ----------------------------------------------------------------------------
 #define TC_BRK_SAMPLES 4096
+#define TC_BRK_TAIL_MAX (1 << 19)   // longest range the collecting sweep redoes itself after a missed bracket
 #define TC_BRK_SLICE 32768   // samples per collecting block (its shared stage holds a quarter of that; measured: 16384 +7 %, 65536 equal, 131072 +30 %)
 
 struct BrkState {
@@ -1104,7 +1129,7 @@ __device__ __forceinline__ uint32_t block_select_smem(const uint32_t *keys, int 
 }
 
 __global__ void __launch_bounds__(1024)
-k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo)
+k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo, int update_here)
 {
     __shared__ uint32_t keys[TC_BRK_SAMPLES];
     __shared__ uint32_t hist[TC_SEL_BINS];
@@ -1154,12 +1179,12 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
         ka = mid - delta >= 0 ? block_select_smem(keys, nk, (uint32_t)(mid - delta), hist, s_wsum, s_scal) : 0u;
         kb = mid + delta < sv ? block_select_smem(keys, nk, (uint32_t)(mid + delta), hist, s_wsum, s_scal) : 0xfffffffeu;
     }
+    double med = NAN;
+    if (exact && sv > 0) med = median_from_pair(key2f(ka), key2f(kb), sv);
     if (tid == 0) {
         BrkState b;
         b.lo = 0; b.hi = 0xfffffffeu; b.n_valid = 0; b.n_below = 0; b.n_in = 0; b.done = 0; b.pad0 = b.pad1 = 0;
         if (exact) {
-            double med = NAN;
-            if (sv > 0) med = median_from_pair(key2f(ka), key2f(kb), sv);
             a.medbuf[range] = med;
             if (a.medians) a.medians[range] = med;
             b.done = 1;
@@ -1171,6 +1196,9 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
         st[range] = b;
         todo[range] = 0;
     }
+    // a launch whose ranges are all settled here (update_here) applies the thresholds as well:
+    // the spectrum stage runs without k_sel_update launches
+    if (update_here && exact) sel_update_span(a, range, med, lo, hi, false);
 }
 
 // radix select of the wanted rank inside the compact buffer.  Runs as the tail of
@@ -1197,6 +1225,16 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
     // the wanted rank (and, for even counts, a lower neighbour) must lie inside the buffer
     if ((int64_t)b.n_in > cap || kth < b.n_below || kth >= b.n_below + b.n_in ||
         (even && kth == b.n_below && b.n_below > 0)) {
+        // the bracket missed (or the buffer overflowed): ranges of moderate length are redone
+        // right here by the plain radix select over the range -- this block is the last one of
+        // its range, the others keep sweeping theirs -- longer ones by the fallback launch
+        const int64_t rlo = a.range_lo[range], rhi = a.range_hi[range];
+        if (rhi - rlo <= TC_BRK_TAIL_MAX) {
+            const float sub = a.sub ? (float)a.sub[range] : 0.0f;
+            const double med = block_range_median(a, rlo, rhi, sub, hist, s_wsum, s_scal);
+            if (tid == 0) { a.medbuf[range] = med; if (a.medians) a.medians[range] = med; }
+            return;
+        }
         if (tid == 0) todo[range] = 1;
         return;
     }
@@ -1425,7 +1463,8 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
 #else
         const int sample_threads = 1024;
 #endif
-        TC_LAUNCH(k_brk_sample, nr, sample_threads, 0, c->stream, b, st + r0, todo + r0);
+        TC_LAUNCH(k_brk_sample, nr, sample_threads, 0, c->stream, b, st + r0, todo + r0,
+                  (small && a.mode != CS_REPORT) ? 1 : 0);
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + a.brk_slice - 1) / a.brk_slice);
@@ -1464,9 +1503,10 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         fprintf(stderr, "[tc select] ranges=%lld max_range=%lld mode=%d fallback=%lld (overflow %lld, miss %lld)\n",
                 (long long)nranges, (long long)max_range, a.mode, (long long)nt, (long long)nover, (long long)nmiss);
     }
-    if (!small) {
+    if (!small && max_range > TC_BRK_TAIL_MAX) {
         // redo the (rare) ranges whose bracket missed with the one-block radix
-        // select; blocks of all other ranges exit at once
+        // select; blocks of all other ranges exit at once (ranges of at most
+        // TC_BRK_TAIL_MAX samples were settled by the collecting sweep's tail)
         ChunkSelectArgs f = a;
         f.todo = todo;
         if (max_range > 64 * TC_SEL_SLICE) {
@@ -1491,7 +1531,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         TC_KERNEL_CHECK();
     }
 fallback_done:
-    if (a.mode != CS_REPORT) {
+    if (a.mode != CS_REPORT && !small) {   // small: k_brk_sample applied the thresholds itself
         tc_prof_begin(c, TCP_CHUNK_SELECT);
         for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
             unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);

@@ -293,3 +293,40 @@ def test_workspace_budget_is_shared_between_thread_contexts(cuda_lib, monkeypatc
         assert np.array_equal(a, want) and np.array_equal(b, want)
     assert sum(held) <= 2048 << 20
     assert max(shares) <= (2048 << 20) // 4
+
+
+_TMA_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import oracle
+from tricolour_b200 import flagging as G
+rs = np.random.RandomState(77)
+worst = 0
+for shape, (r0, r1) in [((2, 64, 256), (5, 8)), ((1, 128, 132), (10, 12)), ((3, 32, 512), (3, 4)), ((1, 48, 96), (11, 1))]:
+    sig = np.array([np.sqrt(((2 * r + 1) ** 2 - 1) / 3.0) + 1e-6 for r in (r0, r1)])
+    for p in range(shape[0]):
+        d = (rs.uniform(size=shape[1:]) * 10 ** rs.uniform(-2, 2, shape[1:])).astype(np.float32)
+        fl = rs.uniform(size=shape[1:]) < 0.3
+        fl[shape[1] // 4:shape[1] // 2, 2:shape[2] // 2] = True
+        o = np.zeros_like(d); o2 = np.zeros_like(d)
+        G.masked_gaussian_filter(d, fl, sig, o)
+        oracle.masked_gaussian_filter(d, fl, sig, o2)
+        worst += int((o.view(np.uint32) != o2.view(np.uint32)).sum() - (np.isnan(o) & np.isnan(o2)).sum())
+print("TMA_DIFF", worst)
+'''
+
+
+def test_tma_form_of_the_second_axis_filter(cuda_lib):
+    """the TMA-staged second-axis filter (k_filter5t.cuh) is opt-in since the plain-load
+    form overtook it: run it in a process of its own (the switch is read once) and
+    compare with the oracle bit for bit"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TC_FILTER_TMA="1", TC_FILTER_TRACE="1")
+    script = _TMA_SCRIPT % {"root": root, "tests": os.path.join(root, "tests")}
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "TMA_DIFF 0" in r.stdout, r.stdout[-500:]
+    assert "b5t filter" in r.stderr, "the TMA form did not run:\n" + r.stderr[-1000:]

@@ -96,18 +96,26 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     const float *fsrc = (MODE_IN == FIN_PAIR && fweight) ? a.win : a.data;
     float4 fq = make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned fg = 0x01010101u;
-    auto fetch = [&](int gi) {
-        const int m = gi * G + 4 * fc;
+    // running pointers: group after group of this lane's chunk (recomputing the addresses from the block
+    // index every iteration cost ~30 instructions per iteration in the compiled loop)
+    const float *fpd = fsrc + fbase + 4 * fc;
+    const u8 *fpg = (MODE_IN == FIN_PAIR ? nullptr : a.flags + fbase + 4 * fc);
+    int fm = 4 * fc;
+    const int fend = fok ? n : 0;
+    auto fetch = [&]() {
         fq = make_float4(0.f, 0.f, 0.f, 0.f);
         fg = 0x01010101u;
-        if (m < n && fok) {
+        if (fm < fend) {
             if (MODE_IN == FIN_PAIR) {
-                fq = *reinterpret_cast<const float4 *>(fsrc + fbase + m);
+                fq = *reinterpret_cast<const float4 *>(fpd);
             } else {
-                if (!INTW) fq = *reinterpret_cast<const float4 *>(a.data + fbase + m);
-                fg = *reinterpret_cast<const unsigned *>(a.flags + fbase + m);
+                if (!INTW) fq = *reinterpret_cast<const float4 *>(fpd);
+                fg = *reinterpret_cast<const unsigned *>(fpg);
             }
         }
+        fm += G;
+        fpd += G;
+        if (MODE_IN != FIN_PAIR) fpg += G;
     };
     auto publish = [&](int vbase) {
         uint4 o;
@@ -157,6 +165,13 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     float o[4];
     unsigned yraw[4];
     bool dbad = false;
+    // the unfiltered samples the residual needs are fetched at the top of the iteration that stores them:
+    // loaded where they are used they cost every warp one exposed DRAM round trip per iteration (ncu source
+    // view: a sixth of the stall samples of a lone warp sat on that one FADD)
+    float2 d2v = make_float2(0.f, 0.f);
+    auto d2_prefetch = [&]() {
+        if (MODE_OUT == FOUT_RESID && (unsigned)js < jsmax) d2v = *reinterpret_cast<const float2 *>(pd2);
+    };
     auto in_q_range = [](float q) { return __float_as_uint(q) - ((127u - 60u) << 23) < (120u << 23); };
     auto drain_math = [&](int buf) {
         const uint4 *row = stage + (buf * GQ + dq) * B5_STAGE_ROW;
@@ -223,9 +238,8 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
                 pw[0] = o[2]; pw[omul] = o[3];
             } else {
                 if (MODE_OUT == FOUT_RESID) {
-                    const float2 d2 = *reinterpret_cast<const float2 *>(pd2);
-                    o[0] = fabsf(d2.x - o[0]);
-                    o[1] = fabsf(d2.y - o[1]);
+                    o[0] = fabsf(d2v.x - o[0]);
+                    o[1] = fabsf(d2v.y - o[1]);
                 }
                 pv[0] = o[0];
                 pv[omul] = o[1];
@@ -251,9 +265,9 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     }
     for (int v = 0; v < nvec; v++) ring[v * 32] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    fetch(0);
+    fetch();
     publish(0);
-    fetch(1);
+    fetch();
     __syncwarp();
 
     const int niter = (n + r4 + G - 1) / G + 3;          // pass 3 finishes local group niter - 4 in the last iteration
@@ -261,7 +275,6 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     // the leaving samples of the next iteration are loaded one iteration ahead whenever they are all older
     // than the group the producer is writing (2r >= G); the entering ones only exist after the __syncwarp
     const bool ahead = r2 >= G;
-    uint4 nxt[GQ];
     auto load_leaving = [&](uint4 *dst) {
         int rq = lv;
 #pragma unroll
@@ -271,22 +284,21 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         }
         lv = rq;
     };
-    if (ahead) load_leaving(nxt);
-    for (int g = 0; g < niter; g++) {
+    // one iteration; `cur` holds the leaving samples of this iteration when they were loaded ahead and
+    // `nx` receives those of the next one.  The loop below is unrolled by two with the roles of the two
+    // buffers swapped, so that no registers are copied between iterations (32 moves per iteration in the
+    // rolled form: a tenth of the loop, ncu source view).
+    auto body = [&](int g, uint4 *cur, uint4 *nx) {
+        d2_prefetch();
         publish(pubv);                                   // group g + 1 of the input
         pubv += GQ; if (pubv == nvec) pubv = 0;
-        fetch(g + 2);
+        fetch();
 
-        uint4 e[GQ], nw[GQ];
+        uint4 e[GQ];
 #pragma unroll
         for (int q = 0; q < GQ; q++) e[q] = ring[(ev + q) * 32];
-        if (ahead) {
-#pragma unroll
-            for (int q = 0; q < GQ; q++) nw[q] = nxt[q];
-            load_leaving(nxt);
-        } else {
-            load_leaving(nw);
-        }
+        if (ahead) load_leaving(nx);
+        else load_leaving(cur);
         drain_math((g - 1) & 1);                         // what pass 3 staged in the previous iteration
         unsigned in[G], old[G], y[G];
 #pragma unroll
@@ -297,14 +309,14 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
             old[0] = car.z; old[1] = car.w;
 #pragma unroll
             for (int q = 0; q < GQ; q++) {
-                old[4 * q + 2] = nw[q].x; old[4 * q + 3] = nw[q].y;
-                if (q + 1 < GQ) { old[4 * q + 4] = nw[q].z; old[4 * q + 5] = nw[q].w; }
+                old[4 * q + 2] = cur[q].x; old[4 * q + 3] = cur[q].y;
+                if (q + 1 < GQ) { old[4 * q + 4] = cur[q].z; old[4 * q + 5] = cur[q].w; }
             }
-            car = nw[GQ - 1];
+            car.z = cur[GQ - 1].z; car.w = cur[GQ - 1].w;
         } else {
 #pragma unroll
             for (int q = 0; q < GQ; q++) {
-                old[4 * q] = nw[q].x; old[4 * q + 1] = nw[q].y; old[4 * q + 2] = nw[q].z; old[4 * q + 3] = nw[q].w;
+                old[4 * q] = cur[q].x; old[4 * q + 1] = cur[q].y; old[4 * q + 2] = cur[q].z; old[4 * q + 3] = cur[q].w;
             }
         }
 #pragma unroll
@@ -326,7 +338,16 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         ev += GQ; if (ev == nvec) ev = 0;
         drain_store();
         __syncwarp();
+    };
+    uint4 bufa[GQ], bufb[GQ];
+    if (ahead) load_leaving(bufa);
+    int g = 0;
+    for (; g + 1 < niter; g += 2) {
+        body(g, bufa, bufb);
+        body(g + 1, bufb, bufa);
     }
+    if (g < niter) body(g, bufa, bufb);
+    d2_prefetch();
     drain_math((niter - 1) & 1);
     drain_store();
 }

@@ -339,8 +339,11 @@ static bool b5t_supported(tc_context *c, const FilterArgs &a)
 {
     // measured on B200 (profiles/r02_filter_probe.txt): ahead of the plain-load form while the rings are short enough for
     // ~18 resident warps per SM (r = 8: 0.92 against 0.96 ms), behind it from r = 17 (11 warps: 1.21 against 1.08 ms)
+    // Since the plain-load form fetches its residual samples an iteration ahead and runs its loop unrolled by
+    // two (k_filter5.cuh), it is ahead at every radius (second axis 122.0 -> 117.8 ms per 32-baseline step with
+    // this form switched off): the TMA form is opt-in, TC_FILTER_TMA=1.
     static const int max_r = tpl_env_int("TC_B5T_MAXR", 12);
-    if (TC_ENV_FLAG("TC_FILTER_NO_TMA") || TC_ENV_FLAG("TC_FILTER_NO_B5") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
+    if (!TC_ENV_FLAG("TC_FILTER_TMA") || TC_ENV_FLAG("TC_FILTER_NO_B5") || TC_ENV_FLAG("TC_FILTER_OLD")) return false;
     if (a.mode_in != FIN_PAIR || (a.mode_out != FOUT_BG && a.mode_out != FOUT_RESID)) return false;
     if (a.r < 1 || a.r > max_r || (a.n & 3) || (a.nj & 3) || a.nlines % a.nj) return false;
     if (a.win <= a.data || ((uintptr_t)a.win - (uintptr_t)a.data) % 16 ||

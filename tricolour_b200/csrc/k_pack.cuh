@@ -306,15 +306,16 @@ k_window_counts(const u8 *__restrict__ flags, int64_t rows_per_bl, int rows_per_
 }
 
 // Vector form (F % 16 == 0): a thread owns 16 adjacent channels, a block of 256 threads a
-// tile of 4096 channels, and walks up to 256 window rows of one baseline with one 16-byte
-// load per row: every row is read fully coalesced.  The 16 column sums of a thread live in
-// eight registers as packed 16-bit fields (256 rows x 255 cannot overflow them).  A block
-// leaves its column sums in its own slice of `partial` (plain stores, no atomics) and adds
-// its total to the baseline with ONE atomic; k_window_counts_fold sums the slices.
-#define TC_WC_ROWS 256
+// tile of 4096 channels, and walks up to TC_WC_ROWS window rows of one baseline with one
+// 16-byte load per row (eight rows in flight): every row is read fully coalesced.  The 16
+// column sums of a thread live in eight registers as packed 16-bit fields (128 rows x 255
+// cannot overflow them).  A block adds its non-zero column sums to the channel counts with
+// 64-bit reductions (consecutive threads, consecutive channels) and its total to the
+// baseline with one more: a single launch, no partial sums in memory.
+#define TC_WC_ROWS 128
 __global__ void __launch_bounds__(256)
-k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, uint32_t *__restrict__ partial,
-                    unsigned long long *__restrict__ bl_counts)
+k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16,
+                    unsigned long long *__restrict__ chan_counts, unsigned long long *__restrict__ bl_counts)
 {
     __shared__ unsigned s_tot[8];
     const int seg = blockIdx.x, tile = blockIdx.y;
@@ -328,14 +329,13 @@ k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, u
     if (f16 < F16) {
         const uint4 *p = flags + (bl * rows_per_bl + row0) * (int64_t)F16 + f16;
         int row = row0;
-        // four rows in flight per trip
-        for (; row + 4 <= row1; row += 4) {
-            uint4 w[4];
+        for (; row + 8 <= row1; row += 8) {
+            uint4 w[8];
 #pragma unroll
-            for (int q = 0; q < 4; q++) w[q] = p[(int64_t)q * F16];
-            p += 4 * (int64_t)F16;
+            for (int q = 0; q < 8; q++) w[q] = p[(int64_t)q * F16];
+            p += 8 * (int64_t)F16;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 8; q++) {
                 acc[0] += w[q].x & 0x00ff00ffu; acc[1] += (w[q].x >> 8) & 0x00ff00ffu;
                 acc[2] += w[q].y & 0x00ff00ffu; acc[3] += (w[q].y >> 8) & 0x00ff00ffu;
                 acc[4] += w[q].z & 0x00ff00ffu; acc[5] += (w[q].z >> 8) & 0x00ff00ffu;
@@ -354,7 +354,7 @@ k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, u
     // column k of the thread: word k / 4, byte k % 4 -> acc[2 * (k / 4) + (k & 1)], field (k % 4) / 2
     unsigned mine = 0;
     if (f16 < F16) {
-        uint32_t *out = partial + (((int64_t)bl * gridDim.x + seg) * F16 + f16) * 16;
+        unsigned long long *out = chan_counts + (int64_t)f16 * 16;
         uint32_t col[16];
 #pragma unroll
         for (int wd = 0; wd < 4; wd++) {
@@ -364,10 +364,10 @@ k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, u
             col[4 * wd + 3] = acc[2 * wd + 1] >> 16;
         }
 #pragma unroll
-        for (int k = 0; k < 16; k++) mine += col[k];
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            reinterpret_cast<uint4 *>(out)[q] = make_uint4(col[4 * q], col[4 * q + 1], col[4 * q + 2], col[4 * q + 3]);
+        for (int k = 0; k < 16; k++) {
+            mine += col[k];
+            if (col[k]) atomicAdd(out + k, (unsigned long long)col[k]);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(TC_FULL_MASK, mine, o);
     if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = mine;
@@ -379,22 +379,3 @@ k_window_counts_v16(const uint4 *__restrict__ flags, int rows_per_bl, int F16, u
     }
 }
 
-// chan_counts[f] = sum over the (baseline, segment) slices; a thread owns one channel,
-// consecutive threads consecutive channels
-__global__ void __launch_bounds__(256)
-k_window_counts_fold(const uint32_t *__restrict__ partial, int64_t nslices, int F,
-                     unsigned long long *__restrict__ chan_counts)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    unsigned long long s = 0;
-    for (int64_t k = 0; k < nslices; k++) s += partial[k * F + f];
-    chan_counts[f] = s;
-}
-
-__global__ void __launch_bounds__(256)
-k_add_u64(unsigned long long *__restrict__ acc, const unsigned long long *__restrict__ x, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) acc[i] += x[i];
-}

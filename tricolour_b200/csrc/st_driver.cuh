@@ -104,10 +104,11 @@ static int dev_masked_filter(tc_context *c, int64_t np, int T, int Fa, const flo
     // the B5 forms (k_filter5.cuh) replace the lane-per-chain kernels of k_filter2.cuh
     // wherever they apply; TC_B5_A_MINR / TC_B5_B_MINR keep an axis on the older forms
     // below a radius (the thread-per-line kernel of small first-axis radii)
-    // (measured on B200, profiles/r02_filter_probe.txt: first axis from r = 37, where the thread-per-line
-    // weight chains stop; second axis up to r ~ 200, beyond which the longer rings cost occupancy)
+    // (measured on B200: first axis from r = 37, where the thread-per-line weight chains stop; second axis
+    // at every radius up to r ~ 200, beyond which the longer rings cost occupancy -- until the residual's
+    // samples were prefetched B5 lost to k_box4 from r = 17 up)
     static const int b5_a_minr = tpl_env_int("TC_B5_A_MINR", 37), b5_b_minr = tpl_env_int("TC_B5_B_MINR", 1);
-    static const int b5_b_maxr = tpl_env_int("TC_B5_B_MAXR", 12);
+    static const int b5_b_maxr = tpl_env_int("TC_B5_B_MAXR", 200);
     probe.n = T; probe.r = (int)r0; probe.data = data_FT; probe.flags = w.fl_FT;
     const bool b5_0 = r0 >= b5_a_minr && r0 > 0 && b5_supported(c, probe);
     probe.n = Fa; probe.r = (int)r1; probe.data = w.v_FT; probe.win = w.w_FT; probe.flags = nullptr;

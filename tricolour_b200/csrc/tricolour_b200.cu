@@ -629,27 +629,15 @@ int tc_window_counts(tc_context *c, const uint8_t *flags, int64_t nbl, int64_t n
         int64_t rows_per_bl = ncorr * T;
         tc_prof_begin(c, TCP_STATS);
         if ((F & 15) == 0 && (((uintptr_t)dfl) & 15) == 0 && rows_per_bl < ((int64_t)1 << 30)) {
-            // 16-byte row reads, per-block slices of column sums, one fold
+            // 16-byte row reads, column sums added to the channel counts by 64-bit reductions: one launch
             const int F16 = (int)(F / 16);
             const unsigned segs = tc_blocks_for(rows_per_bl, TC_WC_ROWS), tiles = tc_blocks_for(F16, 256);
             TC_REQUIRE(tiles <= 65535, "too many channels");
-            for (int64_t b0 = 0; b0 < nbl; b0 += 4096) {
-                const int64_t nb = nbl - b0 < 4096 ? nbl - b0 : 4096;
-                tc_mark mark = tc_arena_mark(c);
-                uint32_t *partial;
-                unsigned long long *dchp = dch;
-                TC_TRY(tc_alloc(c, (size_t)nb * segs * F, &partial));
-                if (b0 > 0) TC_TRY(tc_alloc(c, (size_t)F, &dchp));
+            for (int64_t b0 = 0; b0 < nbl; b0 += 65535) {
+                const int64_t nb = nbl - b0 < 65535 ? nbl - b0 : 65535;
                 TC_LAUNCH(k_window_counts_v16, dim3(segs, tiles, (unsigned)nb), 256, 0, c->stream,
-                          (const uint4 *)(dfl + b0 * rows_per_bl * F), (int)rows_per_bl, F16, partial, dbl + b0);
-                TC_LAUNCH_NOSYNC(k_window_counts_fold, tc_blocks_for(F, 256), 256, 0, c->stream, partial, nb * segs, (int)F,
-                                 dchp);
-                c->launches += 2;
-                if (b0 > 0) {
-                    TC_LAUNCH_NOSYNC(k_add_u64, tc_blocks_for(F, 256), 256, 0, c->stream, dch, dchp, F);
-                    c->launches++;
-                }
-                tc_arena_release(c, mark);
+                          (const uint4 *)(dfl + b0 * rows_per_bl * F), (int)rows_per_bl, F16, dch, dbl + b0);
+                c->launches++;
             }
         } else {
             int rows_per_seg = 64;

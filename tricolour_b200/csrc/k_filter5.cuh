@@ -94,15 +94,17 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     const int64_t fbase = fok ? fline * (int64_t)n : 0;
     const bool fweight = NARR == 2 && fl >= 4;          // this stream is the weight array
     const float *fsrc = (MODE_IN == FIN_PAIR && fweight) ? a.win : a.data;
-    float4 fq = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned fg = 0x01010101u;
+    // two register sets in rotation: a group is fetched two iterations before it is published (one iteration
+    // ahead the publish still waited on the load for a tenth of the first-axis kernel's stall samples)
+    float4 fqa = make_float4(0.f, 0.f, 0.f, 0.f), fqb = fqa;
+    unsigned fga = 0x01010101u, fgb = 0x01010101u;
     // running pointers: group after group of this lane's chunk (recomputing the addresses from the block
     // index every iteration cost ~30 instructions per iteration in the compiled loop)
     const float *fpd = fsrc + fbase + 4 * fc;
     const u8 *fpg = (MODE_IN == FIN_PAIR ? nullptr : a.flags + fbase + 4 * fc);
     int fm = 4 * fc;
     const int fend = fok ? n : 0;
-    auto fetch = [&]() {
+    auto fetch = [&](float4 &fq, unsigned &fg) {
         fq = make_float4(0.f, 0.f, 0.f, 0.f);
         fg = 0x01010101u;
         if (fm < fend) {
@@ -117,7 +119,7 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         fpd += G;
         if (MODE_IN != FIN_PAIR) fpg += G;
     };
-    auto publish = [&](int vbase) {
+    auto publish = [&](int vbase, const float4 &fq, unsigned fg) {
         uint4 o;
         if (MODE_IN == FIN_PAIR) {
             o = make_uint4(__float_as_uint(fq.x), __float_as_uint(fq.y), __float_as_uint(fq.z), __float_as_uint(fq.w));
@@ -265,9 +267,10 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     }
     for (int v = 0; v < nvec; v++) ring[v * 32] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    fetch();
-    publish(0);
-    fetch();
+    fetch(fqa, fga);
+    publish(0, fqa, fga);
+    fetch(fqa, fga);
+    fetch(fqb, fgb);
     __syncwarp();
 
     const int niter = (n + r4 + G - 1) / G + 3;          // pass 3 finishes local group niter - 4 in the last iteration
@@ -288,11 +291,11 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     // `nx` receives those of the next one.  The loop below is unrolled by two with the roles of the two
     // buffers swapped, so that no registers are copied between iterations (32 moves per iteration in the
     // rolled form: a tenth of the loop, ncu source view).
-    auto body = [&](int g, uint4 *cur, uint4 *nx) {
+    auto body = [&](int g, uint4 *cur, uint4 *nx, float4 &fq, unsigned &fg) {
         d2_prefetch();
-        publish(pubv);                                   // group g + 1 of the input
+        publish(pubv, fq, fg);                           // group g + 1 of the input
         pubv += GQ; if (pubv == nvec) pubv = 0;
-        fetch();
+        fetch(fq, fg);                                   // group g + 3
 
         uint4 e[GQ];
 #pragma unroll
@@ -343,10 +346,10 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     if (ahead) load_leaving(bufa);
     int g = 0;
     for (; g + 1 < niter; g += 2) {
-        body(g, bufa, bufb);
-        body(g + 1, bufb, bufa);
+        body(g, bufa, bufb, fqa, fga);
+        body(g + 1, bufb, bufa, fqb, fgb);
     }
-    if (g < niter) body(g, bufa, bufb);
+    if (g < niter) body(g, bufa, bufb, fqa, fga);
     d2_prefetch();
     drain_math((niter - 1) & 1);
     drain_store();

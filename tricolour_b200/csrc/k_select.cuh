@@ -1246,9 +1246,21 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
         const uint32_t dmask = pass == 2 ? 1023u : 2047u;
         for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += nt) {
-            uint32_t k = __ldcg(keys + i);
-            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
+        // eight loads in flight per thread: the buffer of a long range holds ~10^5 keys and this block is
+        // alone with it -- one L2 round trip per key and thread made the tail of the uvcontsub sweeps
+        // (2 Mi-sample ranges) as long as the sweep itself (ncu: 0.42 against 0.24 ms)
+        for (uint32_t i0 = tid; i0 < n; i0 += 8u * nt) {
+            uint32_t kk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t i = i0 + (uint32_t)j * nt;
+                kk[j] = i < n ? __ldcg(keys + i) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t i = i0 + (uint32_t)j * nt;
+                if (i < n && (kk[j] & himask) == prefix) atomicAdd(&hist[(kk[j] >> shift) & dmask], 1u);
+            }
         }
         __syncthreads();
         {
@@ -1291,9 +1303,16 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
         if (tid == 0) s_best = 0;
         __syncthreads();
         uint32_t best = 0;
-        for (uint32_t i = tid; i < n; i += nt) {
-            uint32_t k = __ldcg(keys + i);
-            if (k < prefix && k > best) best = k;
+        for (uint32_t i0 = tid; i0 < n; i0 += 8u * nt) {
+            uint32_t kk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t i = i0 + (uint32_t)j * nt;
+                kk[j] = i < n ? __ldcg(keys + i) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (kk[j] < prefix && kk[j] > best) best = kk[j];
         }
         best = warp_max_u(best);
         if ((tid & 31) == 0 && best) atomicMax(&s_best, best);
@@ -1312,8 +1331,10 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
 // atomic per warp and iteration), then the block reserves its share of the
 // range's buffer with ONE global atomic and copies coalesced.
 #define TC_BRK_STAGE 8192
+// (two blocks of 1024 threads per SM = 32 registers: the sweep lives on occupancy; the select tail and the
+// missed-bracket fallback of the last block may spill)
 template <bool TAKE_ABS, bool SKIP_NAN>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)
 k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict__ cbuf, int64_t cap,
               unsigned *__restrict__ todo)
 {
@@ -1468,8 +1489,10 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + a.brk_slice - 1) / a.brk_slice);
-            static const int env_ct = getenv("TC_BRK_THREADS") ? atoi(getenv("TC_BRK_THREADS")) : 512;
-            const int cthreads = (env_ct == 1024 || env_ct == 256) ? env_ct : 512;   // measured: 512 beats 1024 by 5 %, 256 by 10 %
+            static const int env_ct = getenv("TC_BRK_THREADS") ? atoi(getenv("TC_BRK_THREADS")) : 1024;
+            // measured (chunk_select per 32-baseline step): 1024 threads 68.0 ms, 512 71.7, 256 88.7 -- since the
+            // last block of a range also runs the select tail and the missed-bracket fallback, wider blocks win
+            const int cthreads = (env_ct == 512 || env_ct == 256) ? env_ct : 1024;
             if (b.take_abs && b.skip_nan)
                 TC_LAUNCH((k_brk_collect<true, true>), dim3(cslices, nr), cthreads, 0, c->stream, b, st + r0, cbuf + r0 * cap,
                           cap, todo + r0);

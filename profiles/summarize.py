@@ -112,15 +112,5 @@ if __name__ == "__main__":
     if os.path.exists("%s/%s_other.ncu-rep" % (SRC, TAG)):
         raw(TAG + "_other", "profiles/%s_other_kernels_metrics.csv" % TAG)
         stalls(TAG + "_other", "profiles/%s_other_kernels_stalls.txt" % TAG)
-    # DRAM traffic per launch of the dominant kernel family, for bench.py's roofline.traffic
-    h = rows[0]
-    rd, wr, nm = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
-    unit = rows[1][rd]
-    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
-    # the dominant family: the lane-per-chain kernel of the second filtered axis (k_box4, big launches only)
-    per = [(float(r[rd]) + float(r[wr])) * scale for r in rows[2:]
-           if "k_box4" in r[nm] and (float(r[rd]) + float(r[wr])) * scale > 1e8]
-    json.dump({"kernel": "box_filter (k_box4)", "dram_bytes_per_launch": sum(per) / len(per), "launches_sampled": len(per),
-               "source": "ncu --set full, %s_box_filter.ncu-rep (16 baselines x 4 corr x 512 x 4096 block)" % TAG},
-              open("profiles/%s_traffic.json" % TAG, "w"), indent=1)
+    # (roofline.traffic of bench.py comes from profiles/summarize_traffic.py: every launch of a step)
     print("total ms in launch list:", tot)

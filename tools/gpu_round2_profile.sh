@@ -19,7 +19,7 @@ lists)
   ;;
 box)
   timeout 300 $S > gpurun_out/plain_small.log 2>&1 && \
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_box4|k_box5a|k_box5t|k_box8|k_box_t4a" -s 44 -c 6 -o gpurun_out/r02_box_filter $S > gpurun_out/ncu_full1.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_box4|k_box5a|k_box5b|k_box8|k_box_t4a" -s 44 -c 8 -o gpurun_out/r02_box_filter $S > gpurun_out/ncu_full1.log 2>&1
   echo "full1 rc=$?"
   ;;
 other)

@@ -658,6 +658,7 @@ struct ChunkSelectArgs {
     double *medbuf;           // [nranges] where the sliced paths leave the median for k_sel_update
     float brk_k;              // half width of the sample bracket in units of sqrt(sample size)
     int brk_slice;            // samples per collecting block (multiple of 4096)
+    int brk_tail_max;         // longest range the collecting sweep's last block redoes itself after a missed bracket
 };
 
 #define TC_SEL_BINS 2048
@@ -1229,7 +1230,7 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
         // right here by the plain radix select over the range -- this block is the last one of
         // its range, the others keep sweeping theirs -- longer ones by the fallback launch
         const int64_t rlo = a.range_lo[range], rhi = a.range_hi[range];
-        if (rhi - rlo <= TC_BRK_TAIL_MAX) {
+        if (rhi - rlo <= a.brk_tail_max) {
             const float sub = a.sub ? (float)a.sub[range] : 0.0f;
             const double med = block_range_median(a, rlo, rhi, sub, hist, s_wsum, s_scal);
             if (tid == 0) { a.medbuf[range] = med; if (a.medians) a.medians[range] = med; }
@@ -1464,6 +1465,8 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     static const float env_brk_k = getenv("TC_BRK_K") ? (float)atof(getenv("TC_BRK_K")) : 1.75f;
     a.brk_k = env_brk_k;   // +-3.5 sigma of the sample rank of the median
     a.brk_slice = TC_BRK_SLICE;
+    static const int env_tail_max = getenv("TC_BRK_TAIL_MAX") ? atoi(getenv("TC_BRK_TAIL_MAX")) : TC_BRK_TAIL_MAX;
+    a.brk_tail_max = env_tail_max;
     static const int env_brk_slice = getenv("TC_BRK_SLICE") ? atoi(getenv("TC_BRK_SLICE")) : 0;
     if (env_brk_slice >= 4096 && env_brk_slice <= (1 << 20)) a.brk_slice = env_brk_slice & ~4095;
     const int64_t cap = small ? 1 : max_range / 4 + 4096;
@@ -1489,10 +1492,13 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + a.brk_slice - 1) / a.brk_slice);
-            static const int env_ct = getenv("TC_BRK_THREADS") ? atoi(getenv("TC_BRK_THREADS")) : 1024;
-            // measured (chunk_select per 32-baseline step): 1024 threads 68.0 ms, 512 71.7, 256 88.7 -- since the
-            // last block of a range also runs the select tail and the missed-bracket fallback, wider blocks win
-            const int cthreads = (env_ct == 512 || env_ct == 256) ? env_ct : 1024;
+            static const int env_ct = getenv("TC_BRK_THREADS") ? atoi(getenv("TC_BRK_THREADS")) : 0;
+            // measured (chunk_select per step): 32-baseline blocks 1024 threads 68.0 ms, 512 71.7, 256 88.7;
+            // 64-baseline blocks 1024 threads 128.9, 512 124.3.  The last block of a range also runs the select
+            // tail and the missed-bracket fallback, which wider blocks finish sooner; once the grid is large
+            // enough to hide those tails the finer granularity of 512-thread blocks wins.
+            const int cthreads = (env_ct == 1024 || env_ct == 512 || env_ct == 256) ? env_ct
+                                 : ((int64_t)cslices * nr >= 12288 ? 512 : 1024);
             if (b.take_abs && b.skip_nan)
                 TC_LAUNCH((k_brk_collect<true, true>), dim3(cslices, nr), cthreads, 0, c->stream, b, st + r0, cbuf + r0 * cap,
                           cap, todo + r0);
@@ -1526,7 +1532,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         fprintf(stderr, "[tc select] ranges=%lld max_range=%lld mode=%d fallback=%lld (overflow %lld, miss %lld)\n",
                 (long long)nranges, (long long)max_range, a.mode, (long long)nt, (long long)nover, (long long)nmiss);
     }
-    if (!small && max_range > TC_BRK_TAIL_MAX) {
+    if (!small && max_range > a.brk_tail_max) {
         // redo the (rare) ranges whose bracket missed with the one-block radix
         // select; blocks of all other ranges exit at once (ranges of at most
         // TC_BRK_TAIL_MAX samples were settled by the collecting sweep's tail)

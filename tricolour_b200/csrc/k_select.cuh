@@ -969,17 +969,26 @@ __device__ __forceinline__ void sel_update_span(const ChunkSelectArgs &a, int ra
     const bool vec = allow_vec && ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
     if (vec) {
         const int64_t n4 = (hi - lo) >> 2;
-        for (int64_t q = threadIdx.x; q < n4; q += blockDim.x) {
-            const int64_t i = lo + q * 4;
-            const float4 x = *reinterpret_cast<const float4 *>(a.resid + i);
-            uint32_t nf = ((double)x.x > thr ? 1u : 0u) | ((double)x.y > thr ? 0x100u : 0u) |
-                          ((double)x.z > thr ? 0x10000u : 0u) | ((double)x.w > thr ? 0x1000000u : 0u);
-            uint32_t *fp = reinterpret_cast<uint32_t *>(a.flags + i);
-            if (replace) *fp = nf;
-            else if (nf) {
-                uint32_t old = *fp;
-                // keep bytes 0/1: set byte to 1 where newly flagged
-                *fp = old | nf;
+        // "x > thr" on a float32 sample against the float64 threshold is decided in float32 against the largest
+        // float32 <= thr (the same predicate; NaN never flags), two 16-byte loads in flight per thread
+        const float thrf = __double2float_rd(thr);
+        const float4 *xp = reinterpret_cast<const float4 *>(a.resid + lo);
+        uint32_t *fp0 = reinterpret_cast<uint32_t *>(a.flags + lo);
+        for (int64_t q0 = threadIdx.x; q0 < n4; q0 += 2 * (int64_t)blockDim.x) {
+            float4 x[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int64_t q = q0 + j * (int64_t)blockDim.x;
+                x[j] = q < n4 ? xp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int64_t q = q0 + j * (int64_t)blockDim.x;
+                if (q >= n4) continue;
+                const uint32_t nf = (x[j].x > thrf ? 1u : 0u) | (x[j].y > thrf ? 0x100u : 0u) |
+                                    (x[j].z > thrf ? 0x10000u : 0u) | (x[j].w > thrf ? 0x1000000u : 0u);
+                if (replace) fp0[q] = nf;
+                else if (nf) fp0[q] |= nf;                 // keep bytes 0/1: set byte to 1 where newly flagged
             }
         }
         for (int64_t i = lo + n4 * 4 + threadIdx.x; i < hi; i += blockDim.x) {
@@ -996,7 +1005,7 @@ __device__ __forceinline__ void sel_update_span(const ChunkSelectArgs &a, int ra
     }
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)
 k_sel_update(ChunkSelectArgs a)
 {
     const int range = blockIdx.y;
@@ -1129,6 +1138,68 @@ __device__ __forceinline__ uint32_t block_select_smem(const uint32_t *keys, int 
     return prefix;
 }
 
+// Bracket [ka, kb] of the keys at ranks r_lo <= r_hi among keys[0, n) from TWO histogram passes over the sample
+// instead of two exact three-pass selects: the top 22 bits of both keys are found exactly (one 11-bit histogram
+// serves both ranks, a second one too whenever they share the top digit -- a +-3 % bracket nearly always does),
+// the low 10 bits are rounded outwards.  The bracket only has to contain the median; the collecting sweep
+// counts exactly whatever it is given, so rounding its ends outwards by 2^-13 of their value costs nothing.
+__device__ __forceinline__ void block_bracket_smem(const uint32_t *keys, int n, uint32_t r_lo, uint32_t r_hi,
+                                                   uint32_t *hist, uint32_t *s_wsum, uint32_t *s_scal,
+                                                   uint32_t &ka, uint32_t &kb)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = TC_SEL_BINS / nt;
+    // digit of `rank` in the current histogram, every thread gets (digit, rank inside the digit's bin)
+    auto pick = [&](uint32_t rank, uint32_t &digit, uint32_t &rem) {
+        const uint32_t *mine = hist + tid * per;
+        uint32_t sum = 0;
+        for (int q = 0; q < per; q++) sum += mine[q];
+        uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(TC_FULL_MASK, inc, o);
+            if ((tid & 31) >= o) inc += v;
+        }
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < (tid >> 5); w++) woff += s_wsum[w];
+        const uint32_t excl = woff + inc - sum;
+        if (rank >= excl && rank < excl + sum) {
+            uint32_t acc = excl, d = tid * per;
+            for (int q = 0; q < per; q++) {
+                if (rank < acc + mine[q]) { d = tid * per + q; break; }
+                acc += mine[q];
+            }
+            s_scal[0] = d;
+            s_scal[1] = rank - acc;
+        }
+        __syncthreads();
+        digit = s_scal[0];
+        rem = s_scal[1];
+        __syncthreads();
+    };
+    auto fill = [&](uint32_t prefix, bool top) {
+        for (int q = tid; q < TC_SEL_BINS; q += nt) hist[q] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            const uint32_t k = keys[i];
+            if (top) atomicAdd(&hist[k >> 21], 1u);
+            else if ((k >> 21) == prefix) atomicAdd(&hist[(k >> 10) & 2047u], 1u);
+        }
+        __syncthreads();
+    };
+    uint32_t d_lo, d_hi, m_lo, m_hi, e_lo, e_hi, t;
+    fill(0u, true);
+    pick(r_lo, d_lo, m_lo);
+    pick(r_hi, d_hi, m_hi);
+    fill(d_lo, false);
+    pick(m_lo, e_lo, t);
+    if (d_hi != d_lo) fill(d_hi, false);               // block-uniform
+    pick(m_hi, e_hi, t);
+    ka = (d_lo << 21) | (e_lo << 10);
+    kb = (d_hi << 21) | (e_hi << 10) | 1023u;
+}
+
 __global__ void __launch_bounds__(1024)
 k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict__ todo, int update_here)
 {
@@ -1177,8 +1248,13 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
         const int mid = sv >> 1;
         const int delta = (int)(a.brk_k * sqrtf((float)sv)) + 4;
         bracket = true;
-        ka = mid - delta >= 0 ? block_select_smem(keys, nk, (uint32_t)(mid - delta), hist, s_wsum, s_scal) : 0u;
-        kb = mid + delta < sv ? block_select_smem(keys, nk, (uint32_t)(mid + delta), hist, s_wsum, s_scal) : 0xfffffffeu;
+        if (mid - delta >= 0 && mid + delta < sv) {
+            block_bracket_smem(keys, nk, (uint32_t)(mid - delta), (uint32_t)(mid + delta), hist, s_wsum, s_scal, ka, kb);
+            if (kb > 0xfffffffeu) kb = 0xfffffffeu;
+        } else {
+            ka = mid - delta >= 0 ? block_select_smem(keys, nk, (uint32_t)(mid - delta), hist, s_wsum, s_scal) : 0u;
+            kb = mid + delta < sv ? block_select_smem(keys, nk, (uint32_t)(mid + delta), hist, s_wsum, s_scal) : 0xfffffffeu;
+        }
     }
     double med = NAN;
     if (exact && sv > 0) med = median_from_pair(key2f(ka), key2f(kb), sv);

@@ -137,6 +137,12 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __double2float_rn(double a) { return (float)a; }
+static inline float __double2float_rd(double a)
+{
+    float f = (float)a;
+    if ((double)f > a) f = nextafterf(f, -INFINITY);
+    return f;
+}
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
 static inline void __threadfence() {}

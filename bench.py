@@ -78,6 +78,7 @@ def parse():
     ap.add_argument("--nchan", type=int, default=0)
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes of the CPU sample (0 = one per core)")
     ap.add_argument("--parity-planes", type=int, default=-1, help="planes checked against the oracle (-1 = auto, 0 = off)")
+    ap.add_argument("--clock-interval", type=float, default=0.2, help="seconds between NVML clock samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-light", action="store_true", help="skip the lightly flagged workload (config 1 only)")
@@ -182,9 +183,10 @@ def windows_to_rows(win):
 
 # --------------------------------------------------------------- clocks ------
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    def __init__(self, index, interval=0.2):
         super().__init__(daemon=True)
         self.index = index
+        self.interval = interval
         self.stop_flag = threading.Event()
         self.sm, self.reasons, self.sm_max = [], set(), None
 
@@ -206,7 +208,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if bit and (r & bit):
                         self.reasons.add(nm)
-                time.sleep(0.2)
+                self.stop_flag.wait(self.interval)
         except Exception as e:  # pragma: no cover
             self.reasons.add("sampler_error:%s" % type(e).__name__)
 
@@ -620,7 +622,7 @@ def ours(args):
         return float(t.item()), ctx.launch_count() - l0, out
 
     # ---- device-resident throughput
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_interval)
     # the sampler covers the timed region (warm-up excluded as far as a thread can tell)
     for _ in range(args.warmup):
         w.step_device()

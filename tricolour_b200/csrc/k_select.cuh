@@ -1215,21 +1215,44 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
     __syncthreads();
     const bool exact = len <= TC_BRK_SAMPLES;
     int nv = 0;
-    for (int j = tid; j < TC_BRK_SAMPLES; j += (int)blockDim.x) {
-        uint32_t k = 0xffffffffu;
-        int64_t pos = -1;
-        if (exact) { if (j < len) pos = lo + j; }
-        else {
-            // stratified: one sample per stratum of len / 4096 elements
-            int64_t s0 = (int64_t)j * len / TC_BRK_SAMPLES, s1 = (int64_t)(j + 1) * len / TC_BRK_SAMPLES;
-            int64_t w = s1 - s0 > 0 ? s1 - s0 : 1;
-            pos = lo + s0 + (int64_t)(brk_hash((uint32_t)j * 2654435761u ^ (uint32_t)range) % (uint32_t)w);
+    // four samples per thread and trip, flag and value of each loaded side by side (the value of a flagged
+    // sample is fetched and dropped): eight independent loads in flight instead of two dependent ones
+    for (int j0 = tid; j0 < TC_BRK_SAMPLES; j0 += 4 * (int)blockDim.x) {
+        int64_t pos[4];
+        u8 fl[4];
+        float xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = j0 + q * (int)blockDim.x;
+            pos[q] = -1;
+            if (j < TC_BRK_SAMPLES) {
+                if (exact) { if (j < len) pos[q] = lo + j; }
+                else {
+                    // stratified: one sample per stratum of len / 4096 elements
+                    int64_t s0 = (int64_t)j * len / TC_BRK_SAMPLES, s1 = (int64_t)(j + 1) * len / TC_BRK_SAMPLES;
+                    int64_t w = s1 - s0 > 0 ? s1 - s0 : 1;
+                    pos[q] = lo + s0 + (int64_t)(brk_hash((uint32_t)j * 2654435761u ^ (uint32_t)range) % (uint32_t)w);
+                }
+            }
         }
-        if (pos >= 0 && !a.flags[pos]) {
-            float x = cs_value(a, pos, sub);
-            if (!(a.skip_nan && x != x)) { k = f2key(x); nv++; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            fl[q] = 1;
+            xv[q] = 0.f;
+            if (pos[q] >= 0) { fl[q] = a.flags[pos[q]]; xv[q] = a.resid[pos[q]]; }
         }
-        keys[j] = k;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = j0 + q * (int)blockDim.x;
+            if (j >= TC_BRK_SAMPLES) continue;
+            uint32_t k = 0xffffffffu;
+            if (!fl[q]) {
+                float x = xv[q];
+                if (a.take_abs) x = fabsf(x - sub);
+                if (!(a.skip_nan && x != x)) { k = f2key(x); nv++; }
+            }
+            keys[j] = k;
+        }
     }
     atomicAdd(&s_valid, nv);
     __syncthreads();

@@ -886,3 +886,49 @@ def test_strategy_chain(backend):
     got = common.run_strategies(tb, strategies, vis, flags, ubl, ants, masks, cf, cw)
     want = common.run_strategies(oracle, strategies, vis, flags, ubl, ants, masks, cf, cw)
     assert (got != want).mean() <= 1e-6
+
+
+_MISSED_BRACKET_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import conftest, oracle
+from tricolour_b200 import _cabi
+if %(emu)r:
+    _cabi._set_library_for_testing(_cabi.load(conftest.EMU_LIB))
+from tricolour_b200 import flagging as G
+rs = np.random.RandomState(91)
+bad = 0
+for shape, ce in [((2, 80, 500), [0, 500]), ((1, 96, 520), [0, 130, 520]), ((1, 41, 257), [0, 257])]:
+    d = (rs.standard_normal(shape) * 10 ** rs.uniform(-2, 1, shape)).astype(np.float32)
+    d[0, 3, :9] = 0.25
+    fl = rs.uniform(size=shape) < 0.3
+    for odd in (0, 1):
+        fl[0, 0, 0] = bool(odd)
+        got = np.atleast_2d(G._median_abs(d, fl, ce))
+        for p in range(shape[0]):
+            for k in range(len(ce) - 1):
+                want = oracle._median_abs(d[p][:, ce[k]:ce[k + 1]], fl[p][:, ce[k]:ce[k + 1]])
+                bad += int(got[p, k] != want)
+vis = (rs.standard_normal((2, 2, 48, 256)) + 1j * rs.standard_normal((2, 2, 48, 256))).astype(np.complex64)
+vis[:, :, :, 40] *= 8
+fl = rs.uniform(size=vis.shape) < 0.05
+kw = dict(outlier_nsigma=10, background_iterations=3, num_major_iterations=1)
+bad += int((G.sum_threshold_flagger(vis, fl, **kw) != oracle.sum_threshold_flagger(vis, fl, **kw)).sum())
+print("MISSED_BRACKET_DIFF", bad)
+'''
+
+
+def test_select_missed_bracket_is_redone_by_the_sweep_tail(backend):
+    """TC_BRK_K=0 narrows the sample bracket to a few ranks, so that nearly every range
+    misses it: the last collecting block of the range must then find the exact median
+    itself (block_range_median in the sweep's tail).  The knob is read once per process,
+    hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TC_BRK_K="0.0")
+    script = _MISSED_BRACKET_SCRIPT % {"root": root, "tests": os.path.join(root, "tests"), "emu": backend == "emu"}
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MISSED_BRACKET_DIFF 0" in r.stdout, r.stdout[-500:]

@@ -914,20 +914,31 @@ vis[:, :, :, 40] *= 8
 fl = rs.uniform(size=vis.shape) < 0.05
 kw = dict(outlier_nsigma=10, background_iterations=3, num_major_iterations=1)
 bad += int((G.sum_threshold_flagger(vis, fl, **kw) != oracle.sum_threshold_flagger(vis, fl, **kw)).sum())
+# background loop on ranges longer than the 4096-key sample: the thresholds of such ranges are applied by the
+# block that settles the range (or by k_sel_update when TC_BRK_UPDATE_IN_TAIL=0)
+for shape, it, sw, ce in [((95, 86), 2, (10., 10.), [0, 86]), ((70, 160), 3, (2.5, 4.), [0, 70, 160])]:
+    d = (7.5 + rs.standard_normal(shape) * 0.1).astype(np.float32)
+    d[shape[0] // 3:shape[0] // 2 + 1, 30:80] += 15
+    fl = rs.uniform(size=shape) < 0.05
+    b = G._get_background2d(d, fl, it, np.array(sw), 2.0, np.array(ce))
+    b2 = oracle._get_background2d(d, fl, it, np.array(sw), 2.0, np.array(ce))
+    bad += int((b.view(np.uint32) != b2.view(np.uint32)).sum())
 print("MISSED_BRACKET_DIFF", bad)
 '''
 
 
-def test_select_missed_bracket_is_redone_by_the_sweep_tail(backend):
+@pytest.mark.parametrize("brk_k,update_in_tail", [("0.0", "1"), ("0.0", "0"), ("1.75", "0")])
+def test_select_missed_bracket_is_redone_by_the_sweep_tail(backend, brk_k, update_in_tail):
     """TC_BRK_K=0 narrows the sample bracket to a few ranks, so that nearly every range
     misses it: the last collecting block of the range must then find the exact median
-    itself (block_range_median in the sweep's tail).  The knob is read once per process,
-    hence the subprocess."""
+    itself (block_range_median in the sweep's tail) and, by default, apply the range's
+    threshold too; TC_BRK_UPDATE_IN_TAIL=0 keeps the separate k_sel_update launch.  The
+    knobs are read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, TC_BRK_K="0.0")
+    env = dict(os.environ, TC_BRK_K=brk_k, TC_BRK_UPDATE_IN_TAIL=update_in_tail)
     script = _MISSED_BRACKET_SCRIPT % {"root": root, "tests": os.path.join(root, "tests"), "emu": backend == "emu"}
     r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]

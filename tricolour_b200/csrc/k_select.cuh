@@ -659,6 +659,7 @@ struct ChunkSelectArgs {
     float brk_k;              // half width of the sample bracket in units of sqrt(sample size)
     int brk_slice;            // samples per collecting block (multiple of 4096)
     int brk_tail_max;         // longest range the collecting sweep's last block redoes itself after a missed bracket
+    int update_in_tail;       // the last collecting block of a range applies the range's threshold itself (no k_sel_update launch)
 };
 
 #define TC_SEL_BINS 2048
@@ -1305,9 +1306,10 @@ k_brk_sample(ChunkSelectArgs a, BrkState *__restrict__ st, unsigned *__restrict_
 // the LAST collecting block of a range (every thread of the block calls it);
 // the buffer and the counters were written by other blocks, so they are read
 // past L1.
-__device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const BrkState *st, const uint32_t *cbuf,
+// Returns true when the range's median is settled; `med_out` then holds it in every thread.
+__device__ __forceinline__ bool brk_select_tail(const ChunkSelectArgs &a, const BrkState *st, const uint32_t *cbuf,
                                                 int64_t cap, unsigned *todo, int range, uint32_t *hist,
-                                                uint32_t *s_wsum, uint32_t *s_scal)
+                                                uint32_t *s_wsum, uint32_t *s_scal, double &med_out)
 {
     uint32_t &s_prefix = s_scal[0], &s_remaining = s_scal[1], &s_best = s_scal[2];
     const int tid = threadIdx.x, nt = blockDim.x;   // 256, 512 or 1024 threads
@@ -1318,7 +1320,8 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
     b.n_in = __ldcg(&st[range].n_in);
     if (b.n_valid == 0) {
         if (tid == 0) { a.medbuf[range] = NAN; if (a.medians) a.medians[range] = NAN; }
-        return;
+        med_out = NAN;
+        return true;
     }
     const uint32_t kth = b.n_valid >> 1;
     const bool even = (b.n_valid & 1u) == 0;
@@ -1333,10 +1336,11 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
             const float sub = a.sub ? (float)a.sub[range] : 0.0f;
             const double med = block_range_median(a, rlo, rhi, sub, hist, s_wsum, s_scal);
             if (tid == 0) { a.medbuf[range] = med; if (a.medians) a.medians[range] = med; }
-            return;
+            med_out = med;
+            return true;
         }
         if (tid == 0) todo[range] = 1;
-        return;
+        return false;
     }
     const uint32_t *keys = cbuf + (size_t)range * cap;
     const uint32_t n = b.n_in;
@@ -1419,11 +1423,13 @@ __device__ __forceinline__ void brk_select_tail(const ChunkSelectArgs &a, const 
         __syncthreads();
         lower = key2f(s_best);
     }
+    const double med = median_from_pair(lower, upper, (int)b.n_valid);   // the same value in every thread
     if (tid == 0) {
-        double med = median_from_pair(lower, upper, (int)b.n_valid);
         a.medbuf[range] = med;
         if (a.medians) a.medians[range] = med;
     }
+    med_out = med;
+    return true;
 }
 
 // sweep: count valid / below-bracket keys, copy in-bracket keys to the compact
@@ -1548,7 +1554,14 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     }
     __syncthreads();
     if (!s_last) return;
-    brk_select_tail(a, st, cbuf, cap, todo, range, stage, stage + TC_SEL_BINS, stage + TC_SEL_BINS + 64);
+    double med;
+    const bool settled = brk_select_tail(a, st, cbuf, cap, todo, range, stage, stage + TC_SEL_BINS,
+                                         stage + TC_SEL_BINS + 64, med);
+    // The block that settles a range applies its threshold as well: every other block of the range has
+    // finished (ticket), no other range touches these samples, and the range (a few hundred KB) was read
+    // by this launch moments ago, so the update mostly hits L2 instead of being a second sweep over DRAM
+    // in a launch of its own.
+    if (a.update_in_tail && settled) sel_update_span(a, range, med, a.range_lo[range], a.range_hi[range], true);
 }
 
 static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int64_t nranges, int64_t max_range)
@@ -1566,6 +1579,10 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
     a.brk_slice = TC_BRK_SLICE;
     static const int env_tail_max = getenv("TC_BRK_TAIL_MAX") ? atoi(getenv("TC_BRK_TAIL_MAX")) : TC_BRK_TAIL_MAX;
     a.brk_tail_max = env_tail_max;
+    // ranges the tail can always settle (no fallback launch) get their thresholds from the tail too;
+    // TC_BRK_UPDATE_IN_TAIL=0 keeps the separate k_sel_update launch (A/B knob)
+    static const int env_upd_tail = getenv("TC_BRK_UPDATE_IN_TAIL") ? atoi(getenv("TC_BRK_UPDATE_IN_TAIL")) : 1;
+    a.update_in_tail = (env_upd_tail && !small && a.mode != CS_REPORT && max_range <= a.brk_tail_max) ? 1 : 0;
     static const int env_brk_slice = getenv("TC_BRK_SLICE") ? atoi(getenv("TC_BRK_SLICE")) : 0;
     if (env_brk_slice >= 4096 && env_brk_slice <= (1 << 20)) a.brk_slice = env_brk_slice & ~4095;
     const int64_t cap = small ? 1 : max_range / 4 + 4096;
@@ -1587,7 +1604,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         const int sample_threads = 1024;
 #endif
         TC_LAUNCH(k_brk_sample, nr, sample_threads, 0, c->stream, b, st + r0, todo + r0,
-                  (small && a.mode != CS_REPORT) ? 1 : 0);
+                  ((small || a.update_in_tail) && a.mode != CS_REPORT) ? 1 : 0);
         c->launches++;
         if (!small) {
             unsigned cslices = (unsigned)((max_range + a.brk_slice - 1) / a.brk_slice);
@@ -1659,7 +1676,7 @@ static int launch_bracket_select(tc_context *c, const ChunkSelectArgs &a_in, int
         TC_KERNEL_CHECK();
     }
 fallback_done:
-    if (a.mode != CS_REPORT && !small) {   // small: k_brk_sample applied the thresholds itself
+    if (a.mode != CS_REPORT && !small && !a.update_in_tail) {   // small: k_brk_sample applied the thresholds itself
         tc_prof_begin(c, TCP_CHUNK_SELECT);
         for (int64_t r0 = 0; r0 < nranges; r0 += 65535) {
             unsigned nr = (unsigned)(nranges - r0 < 65535 ? nranges - r0 : 65535);

@@ -328,11 +328,14 @@ class Workload(object):
                    "apply_strategies of tricolour.apps.tricolour.strat_executor over a sequence of blocks, pinned host "
                    "buffers; every block is uploaded, flagged and downloaded inside the timed region, the transfers "
                    "of neighbouring blocks overlap the flagging",
-                2: "host rows -> device, packing.pack_polarised, StrategyExecutor.apply_strategies on the resident "
-                   "windows, flag windows -> host; one block at a time",
+                2: "StrategyExecutor.apply_strategies_pipelined(numpy (row flags, rows) blocks, pre=packing.pack_polarised): "
+                   "host rows -> device, Stokes + pack, strategy on the resident windows, flag windows -> host; "
+                   "the transfers of neighbouring blocks overlap the flagging",
                 3: "StrategyExecutor.apply_strategies_pipelined(numpy (flags, vis) blocks), tasks 4->7",
-                4: "host rows -> device, pack_data, window_stats, apply_strategies, window_stats, "
-                   "unpack_flags_equalised -> host rows, allreduce_window_stats((original, final)) per block",
+                4: "StrategyExecutor.apply_strategies_pipelined(numpy (row flags, rows) blocks, pre=pack_data + "
+                   "window_stats, post=window_stats + unpack_flags_equalised): host rows -> device -> host row flags, "
+                   "allreduce_window_stats((original, final)) per block; transfers of neighbouring blocks overlap "
+                   "the flagging",
                 }[self.idx]
 
     def run_e2e(self, steps):
@@ -349,21 +352,29 @@ class Workload(object):
             for res in self.ex.apply_strategies_pipelined(((self.hf, self.hv) for _ in range(steps)), device=dev.index):
                 pass
         else:
-            for _ in range(steps):
-                rows = torch.from_numpy(self.hv).to(dev, non_blocking=True)
-                rfl = torch.from_numpy(self.hf.view(np.uint8)).to(dev, non_blocking=True).view(torch.bool)
+            # rows -> windows and windows -> rows run inside the executor's pipeline (pre / post hooks on the
+            # flagging stream): the rows of block i+1 are uploaded and the row flags of block i-1 downloaded
+            # while block i is being flagged
+            ub = self.ubl_all[self.bl0:self.bl0 + self.B]
+            stats = []
+
+            def pre(rfl, rows):
                 if self.idx == 2:
                     vw, fw = tb.packing.pack_polarised(self.tinv, self.sub, self.a1, self.a2, rows, rfl, self.T, self.pol)
-                    res = self.ex.apply_strategies(fw, vw).view(torch.uint8).cpu().numpy()
-                else:
-                    ub = self.ubl_all[self.bl0:self.bl0 + self.B]
-                    vw, fw = tb.pack_data(self.tinv, self.sub, self.a1, self.a2, rows, rfl, self.T)
-                    st0 = tb.window_stats(fw, ub, self.cf, self.names, 0, "synthetic", 0)
-                    out = self.ex.apply_strategies(fw, vw)
-                    st1 = tb.window_stats(out, ub, self.cf, self.names, 0, "synthetic", 0)
-                    res = tb.packing.unpack_flags_equalised(self.a1, self.a2, self.tinv, self.sub, out)
-                    res = res.view(torch.uint8).cpu().numpy()
-                    self.reduced = tb.allreduce_window_stats((st0, st1), self.layout)
+                    return fw, vw
+                vw, fw = tb.pack_data(self.tinv, self.sub, self.a1, self.a2, rows, rfl, self.T)
+                stats.append([tb.window_stats(fw, ub, self.cf, self.names, 0, "synthetic", 0)])
+                return fw, vw
+
+            def post(out):
+                stats[-1].append(tb.window_stats(out, ub, self.cf, self.names, 0, "synthetic", 0))
+                return tb.packing.unpack_flags_equalised(self.a1, self.a2, self.tinv, self.sub, out)
+
+            blocks = ((self.hf, self.hv) for _ in range(steps))
+            for res in self.ex.apply_strategies_pipelined(blocks, device=dev.index, pre=pre,
+                                                          post=post if self.idx == 4 else None):
+                if self.idx == 4:
+                    self.reduced = tb.allreduce_window_stats(tuple(stats.pop(0)), self.layout)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         self.e2e_result_shape = tuple(res.shape)

@@ -204,6 +204,56 @@ def test_pipelined_executor_matches_block_by_block(cuda_lib):
 
 
 @pytest.mark.gpu
+def test_pipelined_executor_with_packing_hooks(cuda_lib):
+    """MS rows through the pipelined executor: pre = pack_data, post = unpack + correlation
+    equalisation on the flagging stream; block for block the result of the same calls made
+    one after the other on resident tensors"""
+    import torch
+    nbl, ncorr, T, F = 3, 4, 32, 128
+    ubl = common.baselines(8)[:nbl].copy()
+    ubl[:, 0] = np.arange(nbl)
+    ants = common.antenna_layout(8)
+    cf, cw = common.channels(F)
+    masks = common.synthetic_static_mask(cf)
+    ex = tb.StrategyExecutor(ants, ubl, cf, cw, masks, common.default_strategies()[:4])
+    a1 = np.tile(ubl[:, 1], T).astype(np.int32)
+    a2 = np.tile(ubl[:, 2], T).astype(np.int32)
+    tinv = np.repeat(np.arange(T), nbl)
+
+    def rows_of(w):          # (bl, corr, T, F) -> (row = t * nbl + bl, chan, corr)
+        return np.ascontiguousarray(w.transpose(2, 0, 3, 1).reshape(T * nbl, F, ncorr))
+
+    blocks = []
+    for k in range(4):
+        v, f = common.make_windows(nbl, ncorr, T, F, seed=290 + k, ubl=ubl)
+        blocks.append((rows_of(f), rows_of(v)))
+    seen = []
+
+    def pre(rfl, rows):
+        vw, fw = tb.pack_data(tinv, ubl, a1, a2, rows, rfl, T)
+        seen.append(tuple(fw.shape))
+        return fw, vw
+
+    def post(out):
+        return tb.packing.unpack_flags_equalised(a1, a2, tinv, ubl, out)
+
+    want = []
+    for rf, rv in blocks:
+        out = ex.apply_strategies(*pre(torch.from_numpy(rf).cuda(), torch.from_numpy(rv).cuda()))
+        want.append(post(out).cpu().numpy())
+    got = list(ex.apply_strategies_pipelined(blocks, pre=pre, post=post))
+    assert seen[0] == (nbl, ncorr, T, F)
+    assert len(got) == len(want)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == (T * nbl, F, ncorr) and g.dtype == np.bool_
+        assert np.array_equal(g, w), "block %d" % k
+    # the same executor goes back to plain windows (download buffers follow the result shape)
+    v, f = common.make_windows(nbl, 2, T, F, seed=300, ubl=ubl)
+    plain = list(ex.apply_strategies_pipelined([(f, v)]))
+    assert np.array_equal(plain[0], ex.apply_strategies(f, v))
+
+
+@pytest.mark.gpu
 def test_plane_batching_is_invisible(cuda_lib, monkeypatch):
     """tc_sum_threshold cuts the planes into batches that fit TC_WORKSPACE_MB; the
     flags must not depend on where the cuts fall"""

@@ -88,7 +88,7 @@ class StrategyExecutor(object):
             out = flags.view(torch.uint8).cpu().numpy()
         return out.view(np.bool_) if fdt == np.bool_ else out.astype(fdt)
 
-    def apply_strategies_pipelined(self, blocks, device=None, depth=2):
+    def apply_strategies_pipelined(self, blocks, device=None, depth=2, pre=None, post=None):
         """Flags a sequence of host blocks, overlapping transfers with flagging.
 
         ``blocks`` yields ``(flag_windows, vis_windows)`` numpy pairs (page-locked
@@ -104,6 +104,15 @@ class StrategyExecutor(object):
         for the following block (the executor waits for the block's upload before
         it calls ``next``), so a generator may refill one pair of page-locked
         buffers in place for every block it yields.
+
+        ``pre`` / ``post`` put the packing of the reference's graph inside the same
+        pipeline (app.py:415-432, 479-480): a block may then be any pair of equally
+        shaped (flag, visibility) arrays, e.g. MS rows ``(row, chan, corr)``;
+        ``pre(flags, vis)`` gets the uploaded device tensors and returns the
+        ``(flag_windows, vis_windows)`` to flag (``packing.pack_data`` ...),
+        ``post(flag_windows)`` turns the flagged windows into the device tensor that
+        is downloaded (``packing.unpack_flags_equalised`` ...).  Both run on the
+        flagging stream; whatever else they compute (window statistics) is theirs to keep.
         """
         import torch
         if not torch.cuda.is_available():
@@ -124,9 +133,22 @@ class StrategyExecutor(object):
                     pipe["shape"] = tuple(shape)
                     pipe["f"] = [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(nslots)]
                     pipe["v"] = [torch.empty(shape, dtype=torch.complex64, device=dev) for _ in range(nslots)]
-                    pipe["h"] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True) for _ in range(nslots)]
+                    pipe["h"] = [None] * nslots         # page-locked download buffers, shaped like the results
+                    pipe["hshape"] = None
                     pipe["free"] = [None] * nslots      # event: the slot's device buffers may be overwritten
+                    if pre is None and post is None:
+                        download_buffer(0, shape)       # plain windows: the results have the blocks' shape
                 return pipe
+
+            def download_buffer(slot, shape):
+                # page-locked, shaped like the results; all slots at once the first time a result shape is
+                # seen: page-locking memory is slow (~0.3 ms per MB) and belongs to the first block, not to
+                # the steady state.  Downloads still in flight keep their own reference to the old buffers.
+                shape = tuple(shape)
+                if pipe.get("hshape") != shape or pipe["h"][slot] is None:
+                    pipe["hshape"] = shape
+                    pipe["h"] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True) for _ in range(nslots)]
+                return pipe["h"][slot]
 
             lib = _cabi.load()
             up_ctx = _cabi.get_context(dev.index, int(up_s.cuda_stream))
@@ -163,9 +185,9 @@ class StrategyExecutor(object):
                 return out
 
             def finish(item):
-                slot, ev, fdt, prep = item
+                hbuf, ev, fdt, prep = item
                 out = prep.result()
-                src = pipe["h"][slot].numpy()            # the page-locked buffer is reused
+                src = hbuf.numpy()                       # the page-locked buffer is reused
                 flat_o, flat_s = out.reshape(-1), src.reshape(-1)
                 ev.synchronize()
                 # once the download has landed only a plain copy is left, cut into slices for a
@@ -208,13 +230,22 @@ class StrategyExecutor(object):
                     nxt = upload(next(it), k)      # queued before this block's kernels: overlaps them
                 except StopIteration:
                     nxt = None
-                prep = copier.submit(prepare, tuple(pipe["f"][slot].shape))
+                if pre is None and post is None:
+                    prep = copier.submit(prepare, tuple(pipe["f"][slot].shape))
                 main.wait_event(ev_up)
                 if trace is not None:
                     ev_start = torch.cuda.Event(enable_timing=True)
                     ev_start.record(main)
                     trace.append(("flag %d start" % (k - 1), ev_start))
-                res = self._run(pipe["f"][slot].view(torch.bool), pipe["v"][slot])
+                fw, vw = pipe["f"][slot].view(torch.bool), pipe["v"][slot]
+                if pre is not None:
+                    fw, vw = pre(fw, vw)
+                res = self._run(fw, vw)
+                if post is not None:
+                    res = post(res)
+                res = res.contiguous()
+                if pre is not None or post is not None:
+                    prep = copier.submit(prepare, tuple(res.shape))
                 ev_done = torch.cuda.Event(enable_timing=trace is not None)
                 ev_done.record(main)
                 if trace is not None:
@@ -222,15 +253,16 @@ class StrategyExecutor(object):
                     trace.append(("flag %d done" % (k - 1), ev_done))
                 pipe["free"][slot] = ev_done
                 down_s.wait_event(ev_done)
-                r8 = res.view(torch.uint8)
-                check(lib.tc_memcpy_async(down_ctx.handle, _cabi._vp(pipe["h"][slot].data_ptr()), ptr(r8), int(r8.numel()), 1))
+                r8 = res.view(torch.uint8) if res.dtype == torch.bool else res
+                hbuf = download_buffer(slot, r8.shape)
+                check(lib.tc_memcpy_async(down_ctx.handle, _cabi._vp(hbuf.data_ptr()), ptr(r8), int(r8.numel()), 1))
                 ev_out = torch.cuda.Event(enable_timing=trace is not None)
                 ev_out.record(down_s)
                 if trace is not None:
                     trace.append(("download %d done" % (k - 1), ev_out))
                 res.record_stream(down_s)
                 # the host-side copy out of the page-locked buffer runs on a helper thread
-                pending.append(copier.submit(finish, (slot, ev_out, fdt, prep)))
+                pending.append(copier.submit(finish, (hbuf, ev_out, fdt, prep)))
             while pending:
                 yield pending.pop(0).result()
             if trace is not None:

@@ -87,22 +87,30 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
     // the emits the next pass may see: local indices [ylo, yhi)
     const int ylo = pass == 2 ? r2 : -0x40000000, yhi = pass == 0 ? n + r2 : 0x7fffffff;
 
-    // ---- input role: 16-byte chunk fc of stream fl of every group
+    // ---- input role.  Loading side: lane = ls * 4 + lc fetches the 16-byte chunk lc of stream ls, so the four
+    // chunks of a stream's group are 64 contiguous bytes fetched by four neighbouring lanes (two cache lines per
+    // quarter warp; with lane = chunk * 8 + stream every lane of a quarter warp touched another line: 32 LSU
+    // wavefronts per load instead of 8, on a kernel that runs at ~80 % of the LSU data pipe).  Publishing side:
+    // lane = fc * 8 + fl stores chunk fc of stream fl into the ring of the pass-0 lane fl (conflict-free: the
+    // eight lanes of a quarter warp hit eight different bank groups), after taking it from lane fl * 4 + fc.
+    const int ls = lane >> 2, lc = lane & 3;
     const int fl = lane & 7, fc = lane >> 3;
-    const int64_t fline = grp * NL + (NARR == 1 ? fl : (fl & 3));
+    const int psrc = fl * 4 + fc;
+    const int64_t fline = grp * NL + (NARR == 1 ? ls : (ls & 3));
     const bool fok = fline < a.nlines;
     const int64_t fbase = fok ? fline * (int64_t)n : 0;
-    const bool fweight = NARR == 2 && fl >= 4;          // this stream is the weight array
-    const float *fsrc = (MODE_IN == FIN_PAIR && fweight) ? a.win : a.data;
+    const bool lweight = NARR == 2 && ls >= 4;          // the loaded stream is the weight array
+    const bool fweight = NARR == 2 && fl >= 4;          // the published stream is the weight array
+    const float *fsrc = (MODE_IN == FIN_PAIR && lweight) ? a.win : a.data;
     // two register sets in rotation: a group is fetched two iterations before it is published (one iteration
     // ahead the publish still waited on the load for a tenth of the first-axis kernel's stall samples)
     float4 fqa = make_float4(0.f, 0.f, 0.f, 0.f), fqb = fqa;
     unsigned fga = 0x01010101u, fgb = 0x01010101u;
     // running pointers: group after group of this lane's chunk (recomputing the addresses from the block
     // index every iteration cost ~30 instructions per iteration in the compiled loop)
-    const float *fpd = fsrc + fbase + 4 * fc;
-    const u8 *fpg = (MODE_IN == FIN_PAIR ? nullptr : a.flags + fbase + 4 * fc);
-    int fm = 4 * fc;
+    const float *fpd = fsrc + fbase + 4 * lc;
+    const u8 *fpg = (MODE_IN == FIN_PAIR ? nullptr : a.flags + fbase + 4 * lc);
+    int fm = 4 * lc;
     const int fend = fok ? n : 0;
     auto fetch = [&](float4 &fq, unsigned &fg) {
         fq = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -119,7 +127,17 @@ __device__ __forceinline__ void b5_line_group(const FilterArgs &a, uint4 *wsm, i
         fpd += G;
         if (MODE_IN != FIN_PAIR) fpg += G;
     };
-    auto publish = [&](int vbase, const float4 &fq, unsigned fg) {
+    auto publish = [&](int vbase, const float4 &lq, unsigned lg) {
+        // loading lane -> publishing lane
+        float4 fq = lq;
+        unsigned fg = lg;
+        if (MODE_IN == FIN_PAIR || !INTW) {
+            fq.x = __shfl_sync(TC_FULL_MASK, lq.x, psrc);
+            fq.y = __shfl_sync(TC_FULL_MASK, lq.y, psrc);
+            fq.z = __shfl_sync(TC_FULL_MASK, lq.z, psrc);
+            fq.w = __shfl_sync(TC_FULL_MASK, lq.w, psrc);
+        }
+        if (MODE_IN != FIN_PAIR) fg = __shfl_sync(TC_FULL_MASK, lg, psrc);
         uint4 o;
         if (MODE_IN == FIN_PAIR) {
             o = make_uint4(__float_as_uint(fq.x), __float_as_uint(fq.y), __float_as_uint(fq.z), __float_as_uint(fq.w));

@@ -50,7 +50,7 @@ out = {
     "command": "python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-light --parity-planes 0 "
                "--baselines %d (every launch under ncu --metrics; %g strategy steps in the capture)" % (BASELINES, STEPS),
     "visibilities_per_step": nvis, "launches_per_step_in_capture": tot_l,
-    "launches_note": "every launch of the process divided by the steps: includes torch's input-generation kernels; the library counts its own launches in bench.py's gpu_launches (702 per 8-pass step)", "dram_bytes_per_step": tot_b,
+    "launches_note": "every launch of the process divided by the steps: includes torch's input-generation kernels; the library counts its own launches in bench.py's gpu_launches (672 per 8-pass step)", "dram_bytes_per_step": tot_b,
     "dram_bytes_per_visibility": tot_b / nvis, "algorithmic_bytes_per_visibility": 10,
     "warp_instructions_per_step": tot_i, "thread_instructions_per_visibility": tot_i * 32 / nvis,
     "gpu_time_ms_per_step_under_ncu": tot_ms,

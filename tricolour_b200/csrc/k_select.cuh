@@ -255,17 +255,37 @@ k_line_median2(LineMedianArgs a)
     uint32_t key[VPL];
     float xraw[VPL];
     u8 fraw[VPL];
+    if (a.elem_stride == 1) {
+        // contiguous lines (every caller of the library): one pointer per array, the sample index is an
+        // immediate offset of the load (the 64-bit index products of the general form were a fifth of the
+        // kernel's instructions)
+        const float *pd = a.data + base + lane;
+        const u8 *pf = a.flags ? a.flags + base + lane : nullptr;
+        const u8 *pf2 = a.flags2 ? a.flags2 + base + lane : nullptr;
 #pragma unroll
-    for (int k = 0; k < VPL; k++) {
-        const int i = lane + 32 * k;
-        xraw[k] = 0.f;
-        fraw[k] = 1;
-        if (i < n) {
-            const int64_t idx = base + (int64_t)i * a.elem_stride;
-            xraw[k] = a.data[idx];
-            u8 f = a.flags ? a.flags[idx] : (u8)0;
-            if (a.flags2) f |= a.flags2[idx];
-            fraw[k] = f;
+        for (int k = 0; k < VPL; k++) {
+            xraw[k] = 0.f;
+            fraw[k] = 1;
+            if (lane + 32 * k < n) {
+                xraw[k] = pd[32 * k];
+                u8 f = pf ? pf[32 * k] : (u8)0;
+                if (pf2) f |= pf2[32 * k];
+                fraw[k] = f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const int i = lane + 32 * k;
+            xraw[k] = 0.f;
+            fraw[k] = 1;
+            if (i < n) {
+                const int64_t idx = base + (int64_t)i * a.elem_stride;
+                xraw[k] = a.data[idx];
+                u8 f = a.flags ? a.flags[idx] : (u8)0;
+                if (a.flags2) f |= a.flags2[idx];
+                fraw[k] = f;
+            }
         }
     }
     int cnt = 0;
@@ -311,7 +331,8 @@ k_line_median2(LineMedianArgs a)
         uint32_t d;
         if (round <= 3 || (round & 1)) {
             // rank interpolation; every lane evaluates the same expression on the same values
-            const float f = ((float)(kth - clo) + 0.5f) / (float)(chi - clo);
+            // (an approximate quotient: the trial key only steers the search, every lane computes the same value)
+            const float f = __fdividef((float)(kth - clo) + 0.5f, (float)(chi - clo));
             const float wf = (float)width * f;
             d = wf >= 4294967040.0f ? 0xffffff00u : (uint32_t)wf;
         } else {

@@ -136,6 +136,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline float __double2float_rd(double a)
 {

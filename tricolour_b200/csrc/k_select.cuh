@@ -1480,36 +1480,20 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
     if (tid == 0) { s_valid = 0; s_below = 0; s_in = 0; }
     __syncthreads();
     uint32_t nvalid = 0, nbelow = 0;
-    // four samples per thread and iteration: one 4-byte flag word and one 16-byte
-    // sample vector (the slice start is 4-aligned whenever the range start is)
-    const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
-    const int64_t step = vec ? (int64_t)nt * 4 : nt;
     const unsigned lt = (1u << lane) - 1u;
-    for (int64_t i0 = lo; i0 < hi; i0 += step) {
+    // four samples of one thread: byte q of `fw` is the flag of sample q (slots that do not exist are passed as
+    // flagged), classification, and the warp-level compaction of the in-bracket keys.  Called by every thread of
+    // the block the same number of times.
+    auto process = [&](uint32_t fw, float x0, float x1, float x2, float x3) {
+        const float xv[4] = {x0, x1, x2, x3};
         uint32_t k4[4];
-        bool in4[4] = {false, false, false, false};
-        const int64_t ib = vec ? i0 + (int64_t)tid * 4 : i0 + tid;
-        const int cntv = vec ? 4 : 1;
-        float xv[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t fw = 0x01010101u;
-        if (vec && ib + 3 < hi) {
-            fw = *reinterpret_cast<const uint32_t *>(a.flags + ib);
-            const float4 t4 = *reinterpret_cast<const float4 *>(a.resid + ib);
-            xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
-        } else {
-            fw = 0;
-            for (int q = 0; q < cntv; q++) {
-                const int64_t i = ib + q;
-                if (i < hi) { fw |= (uint32_t)(a.flags[i] ? 1u : 0u) << (8 * q); xv[q] = a.resid[i]; }
-                else fw |= 1u << (8 * q);
-            }
-        }
+        bool in4[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             // predicated, no branches: the modes are template parameters
             float x = xv[q];
             if (TAKE_ABS) x = fabsf(x - sub);
-            bool valid = q < cntv && !((fw >> (8 * q)) & 0xffu);
+            bool valid = !((fw >> (8 * q)) & 0xffu);
             if (SKIP_NAN) valid = valid && !(x != x);
             const uint32_t k = f2key(x);
             const bool below = valid && k < klo;
@@ -1541,6 +1525,47 @@ k_brk_collect(ChunkSelectArgs a, BrkState *__restrict__ st, uint32_t *__restrict
                 if (in4[2]) stage[p2] = k4[2];
                 if (in4[3]) stage[p3] = k4[3];
             }
+        }
+    };
+    // four samples per thread and iteration: one 4-byte flag word and one 16-byte
+    // sample vector (the slice start is 4-aligned whenever the range start is)
+    const bool vec = ((lo & 3) == 0) && ((((uintptr_t)a.resid) & 15) == 0) && ((((uintptr_t)a.flags) & 3) == 0);
+    if (vec) {
+        // iterations in which every thread of the block owns four in-range samples walk two pointers and carry
+        // no bounds tests (the mixed loop had both load forms and their predicates in its body: 227 instructions
+        // per iteration); what is left of the slice goes through one bounds-checked iteration
+        const int64_t len = hi - lo;
+        const int nfull = (int)(len / ((int64_t)nt * 4));
+        const float4 *px = reinterpret_cast<const float4 *>(a.resid + lo) + tid;
+        const uint32_t *pf = reinterpret_cast<const uint32_t *>(a.flags + lo) + tid;
+        for (int it = 0; it < nfull; it++) {
+            const uint32_t fw = *pf;
+            const float4 t4 = *px;
+            pf += nt;
+            px += nt;
+            process(fw, t4.x, t4.y, t4.z, t4.w);
+        }
+        const int64_t i0 = lo + (int64_t)nfull * nt * 4;
+        if (i0 < hi) {                                  // block-uniform
+            const int64_t ib = i0 + (int64_t)tid * 4;
+            uint32_t fw = 0;
+            float xv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int64_t i = ib + q;
+                if (i < hi) { fw |= (uint32_t)(a.flags[i] ? 1u : 0u) << (8 * q); xv[q] = a.resid[i]; }
+                else fw |= 1u << (8 * q);
+            }
+            process(fw, xv[0], xv[1], xv[2], xv[3]);
+        }
+    } else {
+        for (int64_t i0 = lo; i0 < hi; i0 += nt) {
+            const int64_t i = i0 + tid;
+            uint32_t fw = 0x01010100u;                  // one sample per thread, the other three slots do not exist
+            float x = 0.f;
+            if (i < hi) { fw |= a.flags[i] ? 1u : 0u; x = a.resid[i]; }
+            else fw |= 1u;
+            process(fw, x, 0.f, 0.f, 0.f);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

@@ -395,10 +395,57 @@ k_transpose_u8x4(const u8 *__restrict__ in, u8 *__restrict__ out, int R, int C)
     }
 }
 
+// 4-byte planes, R and C multiples of 4: 64 x 64 tiles moved as 16-byte vectors on both sides (four times the
+// bytes in flight per block of the 32 x 32 kernel, which ran at 2.9 TB/s read + write on the float planes)
+__global__ void __launch_bounds__(256)
+k_transpose_w32x4(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int R, int C)
+{
+    __shared__ uint32_t tile[64][65];
+    const int64_t plane = (int64_t)blockIdx.z * R * C;
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = r0 + ty + 16 * k, cc = c0 + 4 * tx;
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < R && cc < C) v[k] = *reinterpret_cast<const uint4 *>(in + plane + (int64_t)r * C + cc);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t *row = &tile[ty + 16 * k][4 * tx];
+        row[0] = v[k].x; row[1] = v[k].y; row[2] = v[k].z; row[3] = v[k].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int cc = c0 + ty + 16 * k, r = r0 + 4 * tx;
+        if (cc < C && r < R) {
+            const int lc = ty + 16 * k;
+            const uint4 w = make_uint4(tile[4 * tx][lc], tile[4 * tx + 1][lc], tile[4 * tx + 2][lc], tile[4 * tx + 3][lc]);
+            *reinterpret_cast<uint4 *>(out + plane + (int64_t)cc * R + r) = w;
+        }
+    }
+}
+
 template <typename T>
 static int launch_transpose(tc_context *c, const T *in, T *out, int64_t nplanes, int R, int C)
 {
     if (nplanes == 0 || R == 0 || C == 0) return TC_OK;
+    if (sizeof(T) == 4 && (R & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0) &&
+        (R + 63) / 64 <= 65535 && !TC_ENV_FLAG("TC_TRANSPOSE_GENERIC")) {
+        for (int64_t p0 = 0; p0 < nplanes; p0 += 65535) {
+            int64_t np = nplanes - p0 < 65535 ? nplanes - p0 : 65535;
+            dim3 grid((C + 63) / 64, (R + 63) / 64, (unsigned)np);
+            tc_prof_begin(c, TCP_TRANSPOSE);
+            TC_LAUNCH(k_transpose_w32x4, grid, 256, 0, c->stream, reinterpret_cast<const uint32_t *>(in) + p0 * R * C,
+                      reinterpret_cast<uint32_t *>(out) + p0 * R * C, R, C);
+            tc_prof_end(c);
+            c->launches++;
+        }
+        TC_KERNEL_CHECK();
+        return TC_OK;
+    }
     if (sizeof(T) == 1 && (R & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)in | (uintptr_t)out) & 3) == 0) &&
         (R + 63) / 64 <= 65535 && !TC_ENV_FLAG("TC_TRANSPOSE_GENERIC")) {
         for (int64_t p0 = 0; p0 < nplanes; p0 += 65535) {

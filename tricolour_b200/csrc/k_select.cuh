@@ -487,6 +487,7 @@ k_line_median_long(LineMedianArgs a)
 // channels; more than 1024 dumps): the same interpolation search with the keys re-read
 // from memory (L1 / L2 hits after the first sweep) in every round -- about eight sweeps
 // instead of the 33 of the bit-per-round form.
+template <bool UNIT>          // UNIT: contiguous lines (elem_stride == 1), 32-bit sample offsets from one pointer per array
 __global__ void __launch_bounds__(128)
 k_line_median2_long(LineMedianArgs a)
 {
@@ -502,8 +503,20 @@ k_line_median2_long(LineMedianArgs a)
     const int n = a.seg_ends ? (int)(a.seg_ends[seg + 1] - s0) : a.n;
     const int64_t base = outer * a.outer_stride + inner * a.inner_stride + s0 * a.elem_stride;
 
-    // key of sample i, or the sentinel when it is flagged
+    // key of sample i, or the sentinel when it is flagged.  UNIT: flag and sample are fetched side by side (no
+    // load waits on another), so that the unrolled sweeps below keep several samples in flight per lane
+    const float *pd = a.data + base;
+    const u8 *pf = a.flags ? a.flags + base : nullptr;
+    const u8 *pf2 = a.flags2 ? a.flags2 + base : nullptr;
     auto key_at = [&](int i) -> uint32_t {
+        if (UNIT) {
+            float x = pd[i];
+            u8 f = pf ? pf[i] : (u8)0;
+            if (pf2) f |= pf2[i];
+            if (a.use_abs) x = fabsf(x);
+            const uint32_t k = f2key(x);
+            return f ? 0xffffffffu : k;
+        }
         const int64_t idx = base + (int64_t)i * a.elem_stride;
         u8 f = a.flags ? a.flags[idx] : (u8)0;
         if (a.flags2) f |= a.flags2[idx];
@@ -514,6 +527,7 @@ k_line_median2_long(LineMedianArgs a)
     };
     int cnt = 0;
     uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll 4
     for (int i = lane; i < n; i += 32) {
         const uint32_t kk = key_at(i);
         if (kk != 0xffffffffu) {
@@ -545,7 +559,7 @@ k_line_median2_long(LineMedianArgs a)
         const uint32_t width = hi - lo;
         uint32_t d;
         if (round <= 3 || (round & 1)) {
-            const float f = ((float)(kth - clo) + 0.5f) / (float)(chi - clo);
+            const float f = __fdividef((float)(kth - clo) + 0.5f, (float)(chi - clo));
             const float wf = (float)width * f;
             d = wf >= 4294967040.0f ? 0xffffff00u : (uint32_t)wf;
         } else {
@@ -556,6 +570,7 @@ k_line_median2_long(LineMedianArgs a)
         const uint32_t t = lo + d;
         int c = 0;
         uint32_t below = 0u, above = 0xffffffffu;
+#pragma unroll 4
         for (int i = lane; i < n; i += 32) {
             const uint32_t kk = key_at(i);
             if (kk < t) { c++; below = kk > below ? kk : below; }
@@ -578,6 +593,7 @@ k_line_median2_long(LineMedianArgs a)
             const int m = chi - clo;
             // at most 32 keys in [lo, hi): gather them one sweep, lane-ordered slots
             int mine = 0;
+#pragma unroll 4
             for (int i = lane; i < n; i += 32) {
                 const uint32_t kk = key_at(i);
                 mine += (kk >= lo && kk < hi) ? 1 : 0;
@@ -631,7 +647,8 @@ static int launch_line_median(tc_context *c, const LineMedianArgs &a, int maxlen
         else if (maxlen <= 512) TC_LAUNCH(k_line_median2<16>, grid, 128, 0, c->stream, a);
         else TC_LAUNCH(k_line_median2<32>, grid, 128, 0, c->stream, a);
     } else if (!TC_ENV_FLAG("TC_MEDIAN_BITS")) {
-        TC_LAUNCH(k_line_median2_long, grid, 128, 0, c->stream, a);
+        if (a.elem_stride == 1) TC_LAUNCH(k_line_median2_long<true>, grid, 128, 0, c->stream, a);
+        else TC_LAUNCH(k_line_median2_long<false>, grid, 128, 0, c->stream, a);
     } else
     if (maxlen <= 128) TC_LAUNCH(k_line_median<4>, grid, 128, 0, c->stream, a);
     else if (maxlen <= 256) TC_LAUNCH(k_line_median<8>, grid, 128, 0, c->stream, a);

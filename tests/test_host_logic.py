@@ -139,3 +139,32 @@ def test_hoisted_reciprocal_division_is_exact_over_its_guard_range():
             q0 = f32(x * rinv)
             q = fma(fma(-q0, d, x), rinv, q0)
             assert q == f32(x / d), (r, ex)
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm the driver launches beside ours) prints ONE JSON
+    line with the keys of the bench contract, runs without a GPU, and does nothing on ranks
+    other than 0 when it is launched under torchrun."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--ntime", "32", "--nchan", "256", "--cpu-planes", "2"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GVis/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["config"]["config_index"] == 1 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GVis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works and prints
+    r1 = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True, text=True,
+                        timeout=600)
+    assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
